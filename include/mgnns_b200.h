@@ -1,0 +1,190 @@
+/*
+ * mgnns_b200.h — C-ABI of the B200-native MGNNS forward/backward hot path.
+ *
+ * One shared object (mgnns_b200/csrc/libmgnns_b200.so, nvcc sm_100a).  Every
+ * entry point takes plain device pointers + sizes + a cudaStream_t passed as
+ * void*; nothing here knows about torch.  The Python host (mgnns_b200/ops.py)
+ * binds these with ctypes and wraps them as torch.library ops ("mgnns::*")
+ * with autograd formulas; see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - all tensors are dense row-major fp32 unless stated, inputs are borrowed
+ *     and never mutated, outputs are caller-allocated;
+ *   - every function returns 0 on success, non-zero on error;
+ *     mgnns_last_error() returns a thread-local message for the last failure;
+ *   - no global mutable state, no hidden synchronisation: kernels are only
+ *     enqueued on `stream`;
+ *   - there is no CPU fallback: a call without a CUDA device fails.
+ *
+ * "ref:" comments cite the reference (YangXiaocui1215/MGNNS) file:line that the
+ * entry point replaces.
+ */
+#ifndef MGNNS_B200_H
+#define MGNNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGNNS_ABI_VERSION 1
+
+/* activation codes for fused epilogues */
+#define MGNNS_ACT_NONE  0
+#define MGNNS_ACT_RELU  1
+#define MGNNS_ACT_LEAKY 2
+
+int         mgnns_abi_version(void);
+const char* mgnns_last_error(void);
+/* number of kernels this library has enqueued in this process (for bench.py's gpu_launches) */
+int64_t     mgnns_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Dense contraction (fp32 CUDA-core path, exact fp32 accumulate).
+ *   C[z] (+)= act( sum_{r<reduce} op(A[z*reduce+r]) * op(B[z*reduce+r]) + bias )
+ *   op(A) is M x K:  transA==0 -> A[m*lda+k],  transA!=0 -> A[k*lda+m]
+ *   op(B) is K x N:  transB==0 -> B[k*ldb+n],  transB!=0 -> B[n*ldb+k]
+ *   batch     : number of (A,B) pairs;  reduce : how many consecutive pairs are
+ *               summed into one C (batch % reduce == 0); C count = batch/reduce
+ *   accumulate: 0 = overwrite C, 1 = atomicAdd into C (C pre-initialised)
+ *   bias      : N floats or NULL;  act: MGNNS_ACT_* (applied after bias;
+ *               not allowed together with accumulate)
+ * ref: torch.matmul at models/Multi_GCN_Multihead_att.py:53,:474,:500,
+ *      nn.Linear at :412,:426,:477-479,:504-506,:563-566,
+ *      models/submodules.py:68-70,:89,:135 (w_qs/w_ks/w_vs/fc/w_1/w_2)
+ * ------------------------------------------------------------------------- */
+int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
+                   const float* A, int64_t lda, int64_t strideA,
+                   const float* B, int64_t ldb, int64_t strideB,
+                   float* C, int64_t ldc, int64_t strideC,
+                   int batch, int reduce, int accumulate,
+                   const float* bias, int act, float slope, void* stream);
+
+/* y = act'(y_saved) * g   (elementwise; backward of a fused activation) */
+int mgnns_act_bwd_f32(const float* y, const float* g, float* out, int64_t n,
+                      int act, float slope, void* stream);
+/* out[n] += sum_m x[m*ld + n]   (bias gradients), out pre-initialised */
+int mgnns_colsum_f32(const float* x, int64_t M, int N, int64_t ld, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * CSR SpMM, sum semiring:  Y[b,i,:] = sum_e val[e] * X[b,col[e],:]
+ *   X: [batch, n_cols, F] with row stride ldx and batch stride strideX
+ *   Y: [batch, n_rows, F] with row stride ldy and batch stride strideY
+ * ref: torch.matmul(adj, support) models/Multi_GCN_Multihead_att.py:54
+ * ------------------------------------------------------------------------- */
+int mgnns_spmm_csr_f32(int n_rows, const int32_t* rowptr, const int32_t* col, const float* val,
+                       const float* X, int64_t ldx, int64_t strideX,
+                       float* Y, int64_t ldy, int64_t strideY,
+                       int F, int batch, void* stream);
+
+/* dense [n,n] fp32 adjacency -> CSR (entries != 0), three steps so the caller
+ * can allocate col/val after reading nnz = rowptr[n]                        */
+int mgnns_dense_row_nnz_f32(const float* A, int n_rows, int n_cols, int64_t ld, int32_t* row_nnz, void* stream);
+int mgnns_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int n, void* stream);
+int mgnns_dense_fill_csr_f32(const float* A, int n_rows, int n_cols, int64_t ld,
+                             const int32_t* rowptr, int32_t* col, float* val, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * TextLevelGCN channel: per document windowed max-aggregation + sum readout.
+ *   doc_ids  int64 [B, L]   (0 = PAD; only the first max_length tokens count)
+ *   node_hidden [V, F], edge_w [n_edge_w] (row 0 = shared "no PMI edge" weight)
+ *   PMI edge-id map in CSR: row s holds sorted dst ids pmi_col[...] and their
+ *   edge ids pmi_eid[...] (NULL -> id = 1 + CSR position, the reference order)
+ *   out [B, F] = (relu?) sum_{v in unique non-PAD words} max_{(u->v)} w_e h[u]
+ * ref: models/Text_GCN.py:142-166 (edges), :168-211 (graph), :242-249 (max
+ *      aggregation), :268-271 (sum readout, ReLU)
+ * ------------------------------------------------------------------------- */
+int mgnns_text_maxagg_fwd(const int64_t* doc_ids, int B, int L, int max_length, int ngram,
+                          const float* node_hidden, int V, int F,
+                          const float* edge_w, int64_t n_edge_w,
+                          const int32_t* pmi_rowptr, const int32_t* pmi_col, const int32_t* pmi_eid,
+                          int apply_relu, float* out, void* stream);
+/* grad_out [B,F]; out = forward output (ReLU mask when apply_relu);
+ * grad_node_hidden [V,F] and grad_edge_w [n_edge_w] are accumulated (atomicAdd) */
+int mgnns_text_maxagg_bwd(const int64_t* doc_ids, int B, int L, int max_length, int ngram,
+                          const float* node_hidden, int V, int F,
+                          const float* edge_w, int64_t n_edge_w,
+                          const int32_t* pmi_rowptr, const int32_t* pmi_col, const int32_t* pmi_eid,
+                          int apply_relu, const float* out, const float* grad_out,
+                          float* grad_node_hidden, float* grad_edge_w, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Single-query multi-head attention core (re-associated form):
+ *   s[b,h,l] = scale * <u[b,h,:], bank[b,l,:]>,  masked (mask[b,l]==0) -> -inf
+ *   p = softmax_l(s);  pt = dropout(p, p_drop, seed)
+ *   ctx[b,h,:] = sum_l pt[b,h,l] * bank[b,l,:];  psum[b,h] = sum_l pt[b,h,l]
+ *   attn[h*B+b, l] = pt   (the reference's head-major [H*B,1,L] layout)
+ *   lse[b,h] = logsumexp_l(s)  (saved for backward)
+ * D % 4 == 0, D <= 512.
+ * ref: models/submodules.py:68-78 (projections folded by the caller), :106-119
+ * ------------------------------------------------------------------------- */
+int mgnns_attn_q1_fwd(const float* u, const float* bank, const float* mask,
+                      int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                      float* ctx, float* attn, float* psum, float* lse, void* stream);
+int mgnns_attn_q1_bwd(const float* u, const float* bank, const float* mask, const float* lse,
+                      const float* grad_ctx, const float* grad_psum /* may be NULL */,
+                      int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                      float* grad_u, float* grad_bank, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Label-query element-wise attention:
+ *   out[b,c,h*dh+d] = dropout(softmax_d(Q[c,h,d]*K[b,h,d]*inv_scale))[d] * V[b,h,d]
+ *   Q [C, heads*dh];  K, V [B, heads*dh] with row stride ldkv
+ * ref: models/Multi_GCN_Multihead_att.py:97-131
+ * ------------------------------------------------------------------------- */
+int mgnns_label_attn_fwd(const float* Q, const float* K, const float* V, int64_t ldkv,
+                         int B, int C, int heads, int dh, float inv_scale,
+                         float p_drop, uint64_t seed, float* out, void* stream);
+/* grad_Q [C,heads*dh] is accumulated (atomicAdd, pre-zeroed by caller);
+ * grad_K / grad_V [B, heads*dh] with row stride ldg are overwritten          */
+int mgnns_label_attn_bwd(const float* Q, const float* K, const float* V, int64_t ldkv,
+                         int B, int C, int heads, int dh, float inv_scale,
+                         float p_drop, uint64_t seed, const float* grad_out,
+                         float* grad_Q, float* grad_K, float* grad_V, int64_t ldg, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Residual add + the reference's custom LayerNorm:
+ *   z = x (+ res);  y = gamma * (z - mean) / (std_unbiased + eps) + beta
+ * ref: models/submodules.py:142-156, call sites :90, :138
+ * ------------------------------------------------------------------------- */
+int mgnns_add_layernorm_fwd(const float* x, const float* res /* may be NULL */,
+                            const float* gamma, const float* beta,
+                            int64_t rows, int D, float eps, float* y, void* stream);
+/* grad_z [rows,D] overwritten (gradient w.r.t. x and res alike);
+ * grad_gamma / grad_beta [D] accumulated (atomicAdd, pre-zeroed by caller)   */
+int mgnns_add_layernorm_bwd(const float* x, const float* res, const float* gamma,
+                            const float* grad_y, int64_t rows, int D, float eps,
+                            float* grad_z, float* grad_gamma, float* grad_beta, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Global spatial max over the trunk feature map  F[B*C, P] -> pooled[B*C],
+ * argmax[B*C] (first maximum, the torch MaxPool2d convention).
+ * ref: nn.MaxPool2d(14,14) models/Multi_GCN_Multihead_att.py:302,:454,:486
+ * ------------------------------------------------------------------------- */
+int mgnns_rowmax_f32(const float* F, int64_t rows, int P, float* pooled, int32_t* argmax, void* stream);
+/* grad_F[r, argmax[r]] += grad_pooled[r]  (grad_F pre-initialised) */
+int mgnns_rowmax_bwd_f32(const float* grad_pooled, const int32_t* argmax, int64_t rows, int P,
+                         float* grad_F, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * PMI co-occurrence counting (integer, bit-exact, order independent).
+ *   tokens int32 [D, L]: vocab index, or -1 for out-of-vocabulary; pad_id is the
+ *   vocab index of the literal 'PAD' token (centre positions equal to pad_id
+ *   are skipped; as a *target* it is counted, as in the reference).
+ *   window: centre i pairs with j in [max(0,i-window), min(L,i+window)), j != i.
+ *   pair_count int32 [V,V] and word_count int64 [V] must be zeroed by the caller.
+ * ref: utils/pmi.py:40-58
+ * ------------------------------------------------------------------------- */
+int mgnns_pmi_count(const int32_t* tokens, int64_t D, int L, int V, int window, int pad_id,
+                    int32_t* pair_count, int64_t* word_count, void* stream);
+/* keep cells with count >= min_count (ref: utils/pmi.py:60-66), row-major order */
+int mgnns_count_row_nnz_i32(const int32_t* M, int n_rows, int n_cols, int min_count,
+                            int32_t* row_nnz, void* stream);
+int mgnns_count_fill_csr_i32(const int32_t* M, int n_rows, int n_cols, int min_count,
+                             const int32_t* rowptr, int32_t* col, int32_t* cnt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGNNS_B200_H */

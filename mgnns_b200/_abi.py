@@ -1,0 +1,91 @@
+"""ctypes binding of the C-ABI declared in include/mgnns_b200.h.
+
+The product path has no CPU fallback: if the shared object is missing and cannot
+be built, importing this module raises; every entry point returns an error code
+that is turned into a RuntimeError carrying mgnns_last_error().
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmgnns_b200.so")
+
+P = c_void_p   # device pointers (and the stream) travel as plain addresses
+
+# name -> (restype, argtypes); mirrors include/mgnns_b200.h line by line
+SIGNATURES = {
+    "mgnns_abi_version": (c_int, []),
+    "mgnns_last_error": (c_char_p, []),
+    "mgnns_launch_count": (c_int64, []),
+    "mgnns_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_int,
+                               P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64,
+                               c_int, c_int, c_int, P, c_int, c_float, P]),
+    "mgnns_act_bwd_f32": (c_int, [P, P, P, c_int64, c_int, c_float, P]),
+    "mgnns_colsum_f32": (c_int, [P, c_int64, c_int, c_int64, P, P]),
+    "mgnns_spmm_csr_f32": (c_int, [c_int, P, P, P, P, c_int64, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
+    "mgnns_dense_row_nnz_f32": (c_int, [P, c_int, c_int, c_int64, P, P]),
+    "mgnns_exclusive_scan_i32": (c_int, [P, P, c_int, P]),
+    "mgnns_dense_fill_csr_f32": (c_int, [P, c_int, c_int, c_int64, P, P, P, P]),
+    "mgnns_text_maxagg_fwd": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int64,
+                                      P, P, P, c_int, P, P]),
+    "mgnns_text_maxagg_bwd": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int64,
+                                      P, P, P, c_int, P, P, P, P, P]),
+    "mgnns_attn_q1_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+                                  P, P, P, P, P]),
+    "mgnns_attn_q1_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+                                  P, P, P]),
+    "mgnns_label_attn_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+                                     P, P]),
+    "mgnns_label_attn_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+                                     P, P, P, P, c_int64, P]),
+    "mgnns_add_layernorm_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, P]),
+    "mgnns_add_layernorm_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, P, P, P]),
+    "mgnns_rowmax_f32": (c_int, [P, c_int64, c_int, P, P, P]),
+    "mgnns_rowmax_bwd_f32": (c_int, [P, P, c_int64, c_int, P, P]),
+    "mgnns_pmi_count": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P]),
+    "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "mgnns_count_fill_csr_i32": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
+}
+# entry points added by optional translation units (tcgen05 paths); bound if present
+OPTIONAL_SIGNATURES = {}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        # building is part of __graft_entry__.build(); try it here so that a fresh
+        # checkout on a box with nvcc works, but never fall back to anything else.
+        try:
+            from .csrc.build import build
+            build()
+        except Exception as exc:  # pragma: no cover - depends on the toolchain
+            raise ImportError(
+                "mgnns_b200: %s is missing and could not be built (%s). "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'`; there is no CPU fallback."
+                % (LIB_PATH, exc))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in OPTIONAL_SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    if lib.mgnns_abi_version() != 1:
+        raise ImportError("mgnns_b200: ABI version mismatch (library %d, binding 1)" % lib.mgnns_abi_version())
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.mgnns_last_error()
+        raise RuntimeError("mgnns_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib.mgnns_launch_count())

@@ -1,0 +1,283 @@
+// fp32 CUDA-core GEMM with fused bias/activation epilogue, strided batch and
+// batch-reduce (split-K over consecutive (A,B) pairs).  This is the exact-fp32
+// contraction used for every small dense op on the path (projections, FFN,
+// classifier tail, label-GCN X*W) and the parity reference for the tcgen05 path.
+//
+// Tile: BM x BN x 16, 256 threads, (4*RM) x (4*RN) outputs per thread, operands
+// staged through shared memory (double buffered, register prefetch), 128-bit
+// global loads whenever the contiguous dimension allows it.
+#include "common.cuh"
+
+namespace mgnns {
+
+struct GemmParams {
+    int M, N, K;
+    const float* A; int64_t lda, strideA;
+    const float* B; int64_t ldb, strideB;
+    float* C; int64_t ldc, strideC;
+    int reduce, accumulate;
+    const float* bias; int act; float slope;
+    int vecA, vecB, vecC;
+};
+
+constexpr int BK = 16;
+constexpr int PAD = 4;
+
+// Load one BMN x BK operand tile into registers (as float4 pieces).
+//   TRANS == false: operand stored [rows=mn][cols=k], k contiguous
+//   TRANS == true : operand stored [rows=k][cols=mn], mn contiguous
+template <int BMN, bool TRANS, int NLD>
+__device__ __forceinline__ void load_tile(float4 (&r)[NLD], const float* __restrict__ P, int64_t ld,
+                                          int mn0, int k0, int MN, int K, int vec, int tid) {
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+        int i = tid + it * 256;
+        int mn, k;
+        if (TRANS) { k = i / (BMN / 4); mn = (i % (BMN / 4)) * 4; }
+        else       { mn = i / (BK / 4); k = (i % (BK / 4)) * 4; }
+        int gmn = mn0 + mn, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TRANS) {
+            if (gk < K) {
+                const float* src = P + (int64_t)gk * ld + gmn;
+                if (vec && gmn + 3 < MN) v = ldg4(src);
+                else {
+                    if (gmn + 0 < MN) v.x = __ldg(src + 0);
+                    if (gmn + 1 < MN) v.y = __ldg(src + 1);
+                    if (gmn + 2 < MN) v.z = __ldg(src + 2);
+                    if (gmn + 3 < MN) v.w = __ldg(src + 3);
+                }
+            }
+        } else {
+            if (gmn < MN) {
+                const float* src = P + (int64_t)gmn * ld + gk;
+                if (vec && gk + 3 < K) v = ldg4(src);
+                else {
+                    if (gk + 0 < K) v.x = __ldg(src + 0);
+                    if (gk + 1 < K) v.y = __ldg(src + 1);
+                    if (gk + 2 < K) v.z = __ldg(src + 2);
+                    if (gk + 3 < K) v.w = __ldg(src + 3);
+                }
+            }
+        }
+        r[it] = v;
+    }
+}
+
+template <int BMN, bool TRANS, int NLD>
+__device__ __forceinline__ void store_tile(const float4 (&r)[NLD], float (*S)[BMN + PAD], int tid) {
+#pragma unroll
+    for (int it = 0; it < NLD; ++it) {
+        int i = tid + it * 256;
+        if (TRANS) {
+            int k = i / (BMN / 4), mn = (i % (BMN / 4)) * 4;
+            *reinterpret_cast<float4*>(&S[k][mn]) = r[it];
+        } else {
+            int mn = i / (BK / 4), k = (i % (BK / 4)) * 4;
+            S[k + 0][mn] = r[it].x;
+            S[k + 1][mn] = r[it].y;
+            S[k + 2][mn] = r[it].z;
+            S[k + 3][mn] = r[it].w;
+        }
+    }
+}
+
+template <int RM, int RN, bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
+    constexpr int BM = 64 * RM, BN = 64 * RN;
+    constexpr int NLA = BM * BK / 4 / 256, NLB = BN * BK / 4 / 256;
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int z = blockIdx.z;
+
+    const int ktiles = (p.K + BK - 1) / BK;
+    const int total = ktiles * p.reduce;
+
+    float acc[4 * RM][4 * RN];
+#pragma unroll
+    for (int i = 0; i < 4 * RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * RN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[NLA], rb[NLB];
+    auto fetch = [&](int t) {
+        int r = t / ktiles, kt = t - r * ktiles;
+        int64_t pair = (int64_t)z * p.reduce + r;
+        // A is indexed by (m, k): TA means stored [k][m]
+        load_tile<BM, TA, NLA>(ra, p.A + pair * p.strideA, p.lda, m0, kt * BK, p.M, p.K, p.vecA, tid);
+        // B is indexed by (k, n): stored [k][n] (n contiguous) unless TB
+        load_tile<BN, !TB, NLB>(rb, p.B + pair * p.strideB, p.ldb, n0, kt * BK, p.N, p.K, p.vecB, tid);
+    };
+
+    fetch(0);
+    store_tile<BM, TA, NLA>(ra, As[0], tid);
+    store_tile<BN, !TB, NLB>(rb, Bs[0], tid);
+    __syncthreads();
+
+    for (int t = 0; t < total; ++t) {
+        const int cur = t & 1;
+        if (t + 1 < total) fetch(t + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4 * RM], b[4 * RN];
+#pragma unroll
+            for (int g = 0; g < RM; ++g) {
+                float4 v = *reinterpret_cast<const float4*>(&As[cur][k][g * 64 + ty * 4]);
+                a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int g = 0; g < RN; ++g) {
+                float4 v = *reinterpret_cast<const float4*>(&Bs[cur][k][g * 64 + tx * 4]);
+                b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4 * RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4 * RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (t + 1 < total) {
+            store_tile<BM, TA, NLA>(ra, As[cur ^ 1], tid);
+            store_tile<BN, !TB, NLB>(rb, Bs[cur ^ 1], tid);
+        }
+        __syncthreads();
+    }
+
+    float* Cz = p.C + (int64_t)z * p.strideC;
+#pragma unroll
+    for (int gi = 0; gi < RM; ++gi)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int row = m0 + gi * 64 + ty * 4 + i;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int gj = 0; gj < RN; ++gj) {
+                int col = n0 + gj * 64 + tx * 4;
+                if (col >= p.N) continue;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float x = acc[gi * 4 + i][gj * 4 + j];
+                    if (p.bias != nullptr && col + j < p.N) x += __ldg(p.bias + col + j);
+                    v[j] = apply_act(x, p.act, p.slope);
+                }
+                float* dst = Cz + (int64_t)row * p.ldc + col;
+                if (p.accumulate) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < p.N) atomicAdd(dst + j, v[j]);
+                } else if (p.vecC && col + 3 < p.N) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < p.N) dst[j] = v[j];
+                }
+            }
+        }
+}
+
+template <int RM, int RN>
+static int launch_gemm(const GemmParams& p, int transA, int transB, int nz, cudaStream_t st) {
+    dim3 grid((p.N + 64 * RN - 1) / (64 * RN), (p.M + 64 * RM - 1) / (64 * RM), nz);
+    if (!transA && !transB) gemm_ffma_kernel<RM, RN, false, false><<<grid, 256, 0, st>>>(p);
+    else if (!transA && transB) gemm_ffma_kernel<RM, RN, false, true><<<grid, 256, 0, st>>>(p);
+    else if (transA && !transB) gemm_ffma_kernel<RM, RN, true, false><<<grid, 256, 0, st>>>(p);
+    else gemm_ffma_kernel<RM, RN, true, true><<<grid, 256, 0, st>>>(p);
+    MG_LAUNCH_CHECK("gemm_ffma");
+    return 0;
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g,
+                               float* __restrict__ out, int64_t n, int act, float slope) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float yy = y[i], gg = g[i];
+        float d = 1.f;
+        if (act == MGNNS_ACT_RELU) d = yy > 0.f ? 1.f : 0.f;
+        else if (act == MGNNS_ACT_LEAKY) d = yy > 0.f ? 1.f : slope;
+        out[i] = gg * d;
+    }
+}
+
+// out[n] += sum_m x[m,n]; block = 32 x 8, each block reduces a strip of rows.
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t M, int N, int64_t ld,
+                              float* __restrict__ out, int rows_per_block) {
+    __shared__ float part[8][33];
+    int n = blockIdx.x * 32 + threadIdx.x;
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float s = 0.f;
+    if (n < N)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + n];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        atomicAdd(out + n, t);
+    }
+}
+
+}  // namespace mgnns
+
+using namespace mgnns;
+
+extern "C" int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
+                              const float* A, int64_t lda, int64_t strideA,
+                              const float* B, int64_t ldb, int64_t strideB,
+                              float* C, int64_t ldc, int64_t strideC,
+                              int batch, int reduce, int accumulate,
+                              const float* bias, int act, float slope, void* stream) {
+    MG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "gemm: negative dimension");
+    MG_REQUIRE(reduce >= 1 && (batch % reduce) == 0, "gemm: batch (%d) must be a multiple of reduce (%d)", batch, reduce);
+    MG_REQUIRE(!(accumulate && (bias != nullptr || act != MGNNS_ACT_NONE)), "gemm: accumulate excludes bias/activation");
+    if (M == 0 || N == 0 || batch == 0) return 0;
+    MG_REQUIRE(A && B && C, "gemm: null operand");
+    MG_REQUIRE(batch / reduce <= 65535, "gemm: too many output batches (%d)", batch / reduce);
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.A = A; p.lda = lda; p.strideA = strideA;
+    p.B = B; p.ldb = ldb; p.strideB = strideB;
+    p.C = C; p.ldc = ldc; p.strideC = strideC;
+    p.reduce = reduce; p.accumulate = accumulate;
+    p.bias = bias; p.act = act; p.slope = slope;
+    p.vecA = aligned16(A) && (lda % 4 == 0) && (strideA % 4 == 0);
+    p.vecB = aligned16(B) && (ldb % 4 == 0) && (strideB % 4 == 0);
+    p.vecC = aligned16(C) && (ldc % 4 == 0) && (strideC % 4 == 0);
+    const int nz = batch / reduce;
+    cudaStream_t st = as_stream(stream);
+    // big tiles only when they still fill the machine
+    int64_t big_ctas = (int64_t)((M + 127) / 128) * ((N + 127) / 128) * nz;
+    if (big_ctas >= 148 * 2) return launch_gemm<2, 2>(p, transA, transB, nz, st);
+    return launch_gemm<1, 1>(p, transA, transB, nz, st);
+}
+
+extern "C" int mgnns_act_bwd_f32(const float* y, const float* g, float* out, int64_t n,
+                                 int act, float slope, void* stream) {
+    if (n == 0) return 0;
+    MG_REQUIRE(y && g && out, "act_bwd: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    act_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(y, g, out, n, act, slope);
+    MG_LAUNCH_CHECK("act_bwd");
+    return 0;
+}
+
+extern "C" int mgnns_colsum_f32(const float* x, int64_t M, int N, int64_t ld, float* out, void* stream) {
+    if (M == 0 || N == 0) return 0;
+    MG_REQUIRE(x && out, "colsum: null pointer");
+    int rows_per_block = 256;
+    int64_t gy = (M + rows_per_block - 1) / rows_per_block;
+    while (gy > 65535) { rows_per_block *= 2; gy = (M + rows_per_block - 1) / rows_per_block; }
+    dim3 grid((N + 31) / 32, (unsigned)gy);
+    colsum_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, M, N, ld, out, rows_per_block);
+    MG_LAUNCH_CHECK("colsum");
+    return 0;
+}

@@ -1,0 +1,680 @@
+"""torch.library ops ("mgnns::*") over the C-ABI, with autograd formulas.
+
+Every op here:
+  * checks device/dtype/contiguity up front and raises on CPU tensors (there is no
+    CPU fallback and no other backend),
+  * allocates its outputs through torch's caching allocator,
+  * enqueues the hand-written kernels on torch's current CUDA stream,
+  * has a fake (meta) implementation, and a backward that is itself made of
+    C-ABI calls.
+"""
+import math
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _abi
+
+_lib = _abi.lib
+_check = _abi.check
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+_LIB = torch.library.Library("mgnns", "DEF")
+
+
+# ----------------------------------------------------------------------------- helpers
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mgnns_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU fallback"
+                               % t.device.type)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError("mgnns_b200: %s must be float32 (got %s)" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D fp32 with unit inner stride (arbitrary row stride)."""
+    if t.dtype != torch.float32:
+        raise RuntimeError("mgnns_b200: %s must be float32 (got %s)" % (name, t.dtype))
+    if t.dim() != 2:
+        raise RuntimeError("mgnns_b200: %s must be 2-D (got %d-D)" % (name, t.dim()))
+    if t.stride(1) != 1 and t.size(1) > 1:
+        t = t.contiguous()
+    if t.size(1) == 1 and t.stride(0) < 1:
+        t = t.contiguous()
+    return t
+
+
+def new_seed() -> int:
+    """Dropout seed drawn from torch's CPU generator (deterministic under torch.manual_seed, no GPU sync)."""
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def gemm_raw(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC,
+             batch=1, reduce=1, accumulate=0, bias=None, act=ACT_NONE, slope=0.0):
+    """Direct call of mgnns_gemm_f32 on device pointers held by tensors A, B, C (+ element offsets)."""
+    a_t, a_off = A if isinstance(A, tuple) else (A, 0)
+    b_t, b_off = B if isinstance(B, tuple) else (B, 0)
+    c_t, c_off = C if isinstance(C, tuple) else (C, 0)
+    _check(_lib.mgnns_gemm_f32(int(transA), int(transB), M, N, K,
+                               a_t.data_ptr() + 4 * a_off, lda, strideA,
+                               b_t.data_ptr() + 4 * b_off, ldb, strideB,
+                               c_t.data_ptr() + 4 * c_off, ldc, strideC,
+                               batch, reduce, accumulate, _ptr(bias), act, float(slope), _stream()), "gemm")
+
+
+# ----------------------------------------------------------------------------- mm
+_LIB.define("mm(Tensor a, Tensor b, Tensor? bias, bool trans_a, bool trans_b, int act, float slope) -> Tensor")
+
+
+def _mm_shapes(a, b, trans_a, trans_b):
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise RuntimeError("mgnns::mm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    return M, N, K
+
+
+def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
+    _need_cuda(a, b, bias)
+    a = _rows2d(a, "a")
+    b = _rows2d(b, "b")
+    M, N, K = _mm_shapes(a, b, trans_a, trans_b)
+    if bias is not None:
+        bias = _f32c(bias, "bias")
+        if bias.numel() != N:
+            raise RuntimeError("mgnns::mm: bias has %d elements, expected %d" % (bias.numel(), N))
+    c = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    gemm_raw(trans_a, trans_b, M, N, K, a, a.stride(0), 0, b, b.stride(0), 0, c, N, 0,
+             bias=bias, act=act, slope=slope)
+    return c
+
+
+def _mm_fake(a, b, bias, trans_a, trans_b, act, slope):
+    M, N, _ = _mm_shapes(a, b, trans_a, trans_b)
+    return a.new_empty((M, N))
+
+
+_LIB.impl("mm", _mm_impl, "CUDA")
+torch.library.register_fake("mgnns::mm", _mm_fake)
+
+
+def act_bwd(y, g, act, slope):
+    if act == ACT_NONE:
+        return g
+    y = _f32c(y, "y")
+    g = _f32c(g, "g")
+    out = torch.empty_like(g)
+    _check(_lib.mgnns_act_bwd_f32(y.data_ptr(), g.data_ptr(), out.data_ptr(), g.numel(), act, float(slope), _stream()),
+           "act_bwd")
+    return out
+
+
+def colsum(x2d):
+    x2d = _rows2d(x2d, "x")
+    out = torch.zeros((x2d.shape[1],), device=x2d.device, dtype=torch.float32)
+    _check(_lib.mgnns_colsum_f32(x2d.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0), out.data_ptr(), _stream()),
+           "colsum")
+    return out
+
+
+def _mm_setup(ctx, inputs, output):
+    a, b, bias, trans_a, trans_b, act, slope = inputs
+    ctx.save_for_backward(a, b, output if act != ACT_NONE else None)
+    ctx.cfg = (trans_a, trans_b, act, slope, bias is not None)
+
+
+def _mm_backward(ctx, g):
+    a, b, y = ctx.saved_tensors
+    ta, tb, act, slope, has_bias = ctx.cfg
+    g = act_bwd(y, g, act, slope) if act != ACT_NONE else _f32c(g, "grad")
+    ga = gb = gbias = None
+    mm = torch.ops.mgnns.mm
+    if ctx.needs_input_grad[0]:
+        ga = mm(g, b, None, False, not tb, ACT_NONE, 0.0) if not ta else mm(b, g, None, tb, True, ACT_NONE, 0.0)
+    if ctx.needs_input_grad[1]:
+        gb = mm(a, g, None, not ta, False, ACT_NONE, 0.0) if not tb else mm(g, a, None, True, ta, ACT_NONE, 0.0)
+    if has_bias and ctx.needs_input_grad[2]:
+        gbias = colsum(g)
+    return ga, gb, gbias, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::mm", _mm_backward, setup_context=_mm_setup)
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, slope=0.0):
+    """act(x @ weight.T + bias) with nn.Linear's [out,in] weight; x may have leading dims."""
+    lead = x.shape[:-1]
+    y = torch.ops.mgnns.mm(x.reshape(-1, x.shape[-1]), weight, bias, False, True, act, slope)
+    return y.reshape(*lead, weight.shape[0])
+
+
+def matmul_nn(x, weight, bias=None, act=ACT_NONE, slope=0.0):
+    """act(x @ weight + bias) with a [in,out] weight (GraphConvolution layout)."""
+    lead = x.shape[:-1]
+    y = torch.ops.mgnns.mm(x.reshape(-1, x.shape[-1]), weight, bias, False, False, act, slope)
+    return y.reshape(*lead, weight.shape[1])
+
+
+# ----------------------------------------------------------------------------- head_mm
+# mode 0: out[b, h*D:(h+1)*D]   = x[b, h*dk:(h+1)*dk] @ w[h*dk:(h+1)*dk, :]        (x [B,H*dk], w [H*dk, D])
+# mode 1: out[b, h*dv:(h+1)*dv] = x[b, h*D:(h+1)*D]   @ w[h*dv:(h+1)*dv, :].T      (x [B,H*D],  w [H*dv, D])
+_LIB.define("head_mm(Tensor x, Tensor w, int heads, int mode) -> Tensor")
+
+
+def _head_mm_impl(x, w, heads, mode):
+    _need_cuda(x, w)
+    x = _f32c(x, "x")
+    w = _f32c(w, "w")
+    B = x.shape[0]
+    D = w.shape[1]
+    dk = w.shape[0] // heads
+    if w.shape[0] != heads * dk:
+        raise RuntimeError("mgnns::head_mm: weight rows not divisible by heads")
+    if mode == 0:
+        if x.shape[1] != heads * dk:
+            raise RuntimeError("mgnns::head_mm: x has %d columns, expected %d" % (x.shape[1], heads * dk))
+        out = torch.empty((B, heads * D), device=x.device, dtype=torch.float32)
+        gemm_raw(0, 0, B, D, dk, x, heads * dk, dk, w, D, dk * D, out, heads * D, D, batch=heads)
+    else:
+        if x.shape[1] != heads * D:
+            raise RuntimeError("mgnns::head_mm: x has %d columns, expected %d" % (x.shape[1], heads * D))
+        out = torch.empty((B, heads * dk), device=x.device, dtype=torch.float32)
+        gemm_raw(0, 1, B, dk, D, x, heads * D, D, w, D, dk * D, out, heads * dk, dk, batch=heads)
+    return out
+
+
+def _head_mm_fake(x, w, heads, mode):
+    D = w.shape[1]
+    dk = w.shape[0] // heads
+    return x.new_empty((x.shape[0], heads * (D if mode == 0 else dk)))
+
+
+_LIB.impl("head_mm", _head_mm_impl, "CUDA")
+torch.library.register_fake("mgnns::head_mm", _head_mm_fake)
+
+
+def _head_mm_setup(ctx, inputs, output):
+    x, w, heads, mode = inputs
+    ctx.save_for_backward(x, w)
+    ctx.cfg = (heads, mode)
+
+
+def _head_mm_backward(ctx, g):
+    x, w = ctx.saved_tensors
+    heads, mode = ctx.cfg
+    g = _f32c(g, "grad")
+    x = _f32c(x, "x")
+    B = x.shape[0]
+    D = w.shape[1]
+    dk = w.shape[0] // heads
+    gx = gw = None
+    if ctx.needs_input_grad[0]:
+        gx = torch.ops.mgnns.head_mm(g, w, heads, 1 - mode)
+    if ctx.needs_input_grad[1]:
+        gw = torch.empty_like(w)
+        if mode == 0:   # gw_h [dk, D] = x_h^T @ g_h
+            gemm_raw(1, 0, dk, D, B, x, heads * dk, dk, g, heads * D, D, gw, D, dk * D, batch=heads)
+        else:           # gw_h [dv, D] = g_h^T @ x_h
+            gemm_raw(1, 0, dk, D, B, g, heads * dk, dk, x, heads * D, D, gw, D, dk * D, batch=heads)
+    return gx, gw, None, None
+
+
+torch.library.register_autograd("mgnns::head_mm", _head_mm_backward, setup_context=_head_mm_setup)
+
+
+# ----------------------------------------------------------------------------- spmm
+_LIB.define("spmm_csr(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor t_rowptr, Tensor t_col, "
+            "Tensor t_val, int n_rows) -> Tensor")
+
+
+def _spmm_raw(rowptr, col, val, x, n_rows):
+    _need_cuda(rowptr, col, val, x)
+    x = _f32c(x, "x")
+    if x.dim() == 2:
+        batch, n_cols, F = 1, x.shape[0], x.shape[1]
+        y = torch.empty((n_rows, F), device=x.device, dtype=torch.float32)
+    elif x.dim() == 3:
+        batch, n_cols, F = x.shape
+        y = torch.empty((batch, n_rows, F), device=x.device, dtype=torch.float32)
+    else:
+        raise RuntimeError("mgnns::spmm_csr: x must be [N,F] or [B,N,F]")
+    if rowptr.dtype != torch.int32 or col.dtype != torch.int32 or val.dtype != torch.float32:
+        raise RuntimeError("mgnns::spmm_csr: CSR arrays must be int32/int32/float32")
+    if rowptr.numel() != n_rows + 1:
+        raise RuntimeError("mgnns::spmm_csr: rowptr has %d entries, expected %d" % (rowptr.numel(), n_rows + 1))
+    for b0 in range(0, batch, 65535):
+        nb = min(65535, batch - b0)
+        _check(_lib.mgnns_spmm_csr_f32(n_rows, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                       x.data_ptr() + 4 * b0 * n_cols * F, F, n_cols * F,
+                                       y.data_ptr() + 4 * b0 * n_rows * F, F, n_rows * F,
+                                       F, nb, _stream()), "spmm_csr")
+    return y
+
+
+def _spmm_impl(rowptr, col, val, x, t_rowptr, t_col, t_val, n_rows):
+    return _spmm_raw(rowptr, col, val, x, n_rows)
+
+
+def _spmm_fake(rowptr, col, val, x, t_rowptr, t_col, t_val, n_rows):
+    shape = list(x.shape)
+    shape[-2] = n_rows
+    return x.new_empty(shape)
+
+
+_LIB.impl("spmm_csr", _spmm_impl, "CUDA")
+torch.library.register_fake("mgnns::spmm_csr", _spmm_fake)
+
+
+def _spmm_setup(ctx, inputs, output):
+    rowptr, col, val, x, t_rowptr, t_col, t_val, n_rows = inputs
+    ctx.save_for_backward(t_rowptr, t_col, t_val)
+    ctx.n_cols = x.shape[-2]
+
+
+def _spmm_backward(ctx, g):
+    t_rowptr, t_col, t_val = ctx.saved_tensors
+    gx = None
+    if ctx.needs_input_grad[3]:
+        gx = _spmm_raw(t_rowptr, t_col, t_val, g, ctx.n_cols)
+    return None, None, None, gx, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::spmm_csr", _spmm_backward, setup_context=_spmm_setup)
+
+
+# ----------------------------------------------------------------------------- dense -> CSR
+def dense_to_csr(adj: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """[n,m] fp32 CUDA matrix -> (rowptr int32[n+1], col int32[nnz], val fp32[nnz]); one host sync for nnz."""
+    _need_cuda(adj)
+    adj = _rows2d(adj, "adj")
+    n, m = adj.shape
+    nnz_row = torch.empty((n,), device=adj.device, dtype=torch.int32)
+    rowptr = torch.empty((n + 1,), device=adj.device, dtype=torch.int32)
+    s = _stream()
+    _check(_lib.mgnns_dense_row_nnz_f32(adj.data_ptr(), n, m, adj.stride(0), nnz_row.data_ptr(), s), "dense_row_nnz")
+    _check(_lib.mgnns_exclusive_scan_i32(nnz_row.data_ptr(), rowptr.data_ptr(), n, s), "scan")
+    nnz = int(rowptr[-1].item())
+    col = torch.empty((max(nnz, 1),), device=adj.device, dtype=torch.int32)[:nnz]
+    val = torch.empty((max(nnz, 1),), device=adj.device, dtype=torch.float32)[:nnz]
+    _check(_lib.mgnns_dense_fill_csr_f32(adj.data_ptr(), n, m, adj.stride(0), rowptr.data_ptr(),
+                                         col.data_ptr(), val.data_ptr(), s), "dense_fill_csr")
+    return rowptr, col, val
+
+
+# ----------------------------------------------------------------------------- text max-aggregation
+_LIB.define("text_maxagg(Tensor doc_ids, Tensor node_hidden, Tensor edge_w, Tensor pmi_rowptr, Tensor pmi_col, "
+            "Tensor? pmi_eid, int ngram, int max_length, bool apply_relu) -> Tensor")
+
+
+def _text_args(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid):
+    _need_cuda(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid)
+    if doc_ids.dtype != torch.int64 or doc_ids.dim() != 2:
+        raise RuntimeError("mgnns::text_maxagg: doc_ids must be int64 [B,L]")
+    doc_ids = doc_ids.contiguous()
+    node_hidden = _f32c(node_hidden, "node_hidden")
+    edge_w = _f32c(edge_w, "edge_w")
+    if pmi_rowptr.dtype != torch.int32 or pmi_col.dtype != torch.int32:
+        raise RuntimeError("mgnns::text_maxagg: PMI CSR arrays must be int32")
+    if pmi_rowptr.numel() != node_hidden.shape[0] + 1:
+        raise RuntimeError("mgnns::text_maxagg: pmi_rowptr must have V+1 entries")
+    if pmi_eid is not None and pmi_eid.dtype != torch.int32:
+        raise RuntimeError("mgnns::text_maxagg: pmi_eid must be int32")
+    return doc_ids, node_hidden, edge_w
+
+
+def _text_impl(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid, ngram, max_length, apply_relu):
+    doc_ids, node_hidden, edge_w = _text_args(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid)
+    B, L = doc_ids.shape
+    V, F = node_hidden.shape
+    out = torch.empty((B, F), device=node_hidden.device, dtype=torch.float32)
+    _check(_lib.mgnns_text_maxagg_fwd(doc_ids.data_ptr(), B, L, max_length, ngram, node_hidden.data_ptr(), V, F,
+                                      edge_w.data_ptr(), edge_w.numel(), pmi_rowptr.data_ptr(), pmi_col.data_ptr(),
+                                      _ptr(pmi_eid), int(apply_relu), out.data_ptr(), _stream()), "text_maxagg_fwd")
+    return out
+
+
+def _text_fake(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid, ngram, max_length, apply_relu):
+    return node_hidden.new_empty((doc_ids.shape[0], node_hidden.shape[1]))
+
+
+_LIB.impl("text_maxagg", _text_impl, "CUDA")
+torch.library.register_fake("mgnns::text_maxagg", _text_fake)
+
+
+def _text_setup(ctx, inputs, output):
+    doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid, ngram, max_length, apply_relu = inputs
+    ctx.save_for_backward(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid, output)
+    ctx.cfg = (ngram, max_length, apply_relu)
+
+
+def _text_backward(ctx, g):
+    doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid, out = ctx.saved_tensors
+    ngram, max_length, apply_relu = ctx.cfg
+    doc_ids, node_hidden, edge_w_c = _text_args(doc_ids, node_hidden, edge_w, pmi_rowptr, pmi_col, pmi_eid)
+    g = _f32c(g, "grad")
+    B, L = doc_ids.shape
+    V, F = node_hidden.shape
+    g_h = torch.zeros_like(node_hidden)
+    g_w = torch.zeros((edge_w_c.numel(),), device=g.device, dtype=torch.float32)
+    _check(_lib.mgnns_text_maxagg_bwd(doc_ids.data_ptr(), B, L, max_length, ngram, node_hidden.data_ptr(), V, F,
+                                      edge_w_c.data_ptr(), edge_w_c.numel(), pmi_rowptr.data_ptr(),
+                                      pmi_col.data_ptr(), _ptr(pmi_eid), int(apply_relu), out.data_ptr(),
+                                      g.data_ptr(), g_h.data_ptr(), g_w.data_ptr(), _stream()), "text_maxagg_bwd")
+    return None, g_h, g_w.view_as(edge_w), None, None, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::text_maxagg", _text_backward, setup_context=_text_setup)
+
+
+# ----------------------------------------------------------------------------- single-query attention core
+_LIB.define("attn_q1(Tensor u, Tensor bank, Tensor? mask, float scale, float p_drop, int seed) "
+            "-> (Tensor, Tensor, Tensor, Tensor)")
+
+
+def _attn_check(u, bank, mask):
+    _need_cuda(u, bank, mask)
+    u = _f32c(u, "u")
+    bank = _f32c(bank, "bank")
+    if u.dim() != 3 or bank.dim() != 3 or u.shape[0] != bank.shape[0] or u.shape[2] != bank.shape[2]:
+        raise RuntimeError("mgnns::attn_q1: expected u [B,H,D] and bank [B,L,D]")
+    if mask is not None:
+        mask = _f32c(mask, "mask")
+        if mask.shape != bank.shape[:2]:
+            raise RuntimeError("mgnns::attn_q1: mask must be [B,L]")
+    return u, bank, mask
+
+
+def _attn_impl(u, bank, mask, scale, p_drop, seed):
+    u, bank, mask = _attn_check(u, bank, mask)
+    B, H, D = u.shape
+    L = bank.shape[1]
+    ctx = torch.empty((B, H, D), device=u.device, dtype=torch.float32)
+    attn = torch.empty((H * B, 1, L), device=u.device, dtype=torch.float32)
+    psum = torch.empty((B, H), device=u.device, dtype=torch.float32)
+    lse = torch.empty((B, H), device=u.device, dtype=torch.float32)
+    _check(_lib.mgnns_attn_q1_fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale), float(p_drop),
+                                  seed & 0xFFFFFFFFFFFFFFFF, ctx.data_ptr(), attn.data_ptr(), psum.data_ptr(),
+                                  lse.data_ptr(), _stream()), "attn_q1_fwd")
+    return ctx, attn, psum, lse
+
+
+def _attn_fake(u, bank, mask, scale, p_drop, seed):
+    B, H, D = u.shape
+    L = bank.shape[1]
+    return u.new_empty((B, H, D)), u.new_empty((H * B, 1, L)), u.new_empty((B, H)), u.new_empty((B, H))
+
+
+_LIB.impl("attn_q1", _attn_impl, "CUDA")
+torch.library.register_fake("mgnns::attn_q1", _attn_fake)
+
+
+def _attn_setup(ctx, inputs, output):
+    u, bank, mask, scale, p_drop, seed = inputs
+    ctx.save_for_backward(u, bank, mask, output[3])
+    ctx.cfg = (scale, p_drop, seed)
+
+
+def _attn_backward(ctx, g_ctx, g_attn, g_psum, g_lse):
+    u, bank, mask, lse = ctx.saved_tensors
+    scale, p_drop, seed = ctx.cfg
+    u, bank, mask = _attn_check(u, bank, mask)
+    B, H, D = u.shape
+    L = bank.shape[1]
+    g_ctx = torch.zeros_like(u) if g_ctx is None else _f32c(g_ctx, "grad_ctx")
+    g_psum = None if g_psum is None else _f32c(g_psum, "grad_psum")
+    gu = torch.empty_like(u)
+    gbank = torch.empty_like(bank)
+    _check(_lib.mgnns_attn_q1_bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
+                                  _ptr(g_psum), B, H, L, D, float(scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
+                                  gu.data_ptr(), gbank.data_ptr(), _stream()), "attn_q1_bwd")
+    return gu, gbank, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::attn_q1", _attn_backward, setup_context=_attn_setup)
+
+
+# ----------------------------------------------------------------------------- label attention
+_LIB.define("label_attn(Tensor q, Tensor kv, int heads, float inv_scale, float p_drop, int seed) -> Tensor")
+
+
+def _label_check(q, kv, heads):
+    _need_cuda(q, kv)
+    q = _f32c(q, "q")
+    kv = _f32c(kv, "kv")
+    HD = q.shape[1]
+    if kv.dim() != 2 or kv.shape[1] != 2 * HD or HD % heads != 0:
+        raise RuntimeError("mgnns::label_attn: expected q [C,HD], kv [B,2*HD], HD divisible by heads")
+    return q, kv, HD
+
+
+def _label_impl(q, kv, heads, inv_scale, p_drop, seed):
+    q, kv, HD = _label_check(q, kv, heads)
+    B, C = kv.shape[0], q.shape[0]
+    out = torch.empty((B, C, HD), device=q.device, dtype=torch.float32)
+    _check(_lib.mgnns_label_attn_fwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD, 2 * HD, B, C, heads,
+                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
+                                     out.data_ptr(), _stream()), "label_attn_fwd")
+    return out
+
+
+def _label_fake(q, kv, heads, inv_scale, p_drop, seed):
+    return q.new_empty((kv.shape[0], q.shape[0], q.shape[1]))
+
+
+_LIB.impl("label_attn", _label_impl, "CUDA")
+torch.library.register_fake("mgnns::label_attn", _label_fake)
+
+
+def _label_setup(ctx, inputs, output):
+    q, kv, heads, inv_scale, p_drop, seed = inputs
+    ctx.save_for_backward(q, kv)
+    ctx.cfg = (heads, inv_scale, p_drop, seed)
+
+
+def _label_backward(ctx, g):
+    q, kv = ctx.saved_tensors
+    heads, inv_scale, p_drop, seed = ctx.cfg
+    q, kv, HD = _label_check(q, kv, heads)
+    g = _f32c(g, "grad")
+    B, C = kv.shape[0], q.shape[0]
+    gq = torch.zeros_like(q)
+    gkv = torch.empty_like(kv)
+    _check(_lib.mgnns_label_attn_bwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD, 2 * HD, B, C, heads,
+                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
+                                     g.data_ptr(), gq.data_ptr(), gkv.data_ptr(), gkv.data_ptr() + 4 * HD, 2 * HD,
+                                     _stream()), "label_attn_bwd")
+    return gq, gkv, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::label_attn", _label_backward, setup_context=_label_setup)
+
+
+# ----------------------------------------------------------------------------- add + LayerNorm
+_LIB.define("add_layernorm(Tensor x, Tensor? res, Tensor gamma, Tensor beta, float eps) -> Tensor")
+
+
+def _ln_impl(x, res, gamma, beta, eps):
+    _need_cuda(x, res, gamma, beta)
+    x = _f32c(x, "x")
+    res = None if res is None else _f32c(res, "res")
+    gamma = _f32c(gamma, "gamma")
+    beta = _f32c(beta, "beta")
+    D = x.shape[-1]
+    if gamma.numel() != D or beta.numel() != D or (res is not None and res.shape != x.shape):
+        raise RuntimeError("mgnns::add_layernorm: shape mismatch")
+    y = torch.empty_like(x)
+    _check(_lib.mgnns_add_layernorm_fwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), beta.data_ptr(),
+                                        x.numel() // D, D, float(eps), y.data_ptr(), _stream()), "add_layernorm_fwd")
+    return y
+
+
+def _ln_fake(x, res, gamma, beta, eps):
+    return torch.empty_like(x)
+
+
+_LIB.impl("add_layernorm", _ln_impl, "CUDA")
+torch.library.register_fake("mgnns::add_layernorm", _ln_fake)
+
+
+def _ln_setup(ctx, inputs, output):
+    x, res, gamma, beta, eps = inputs
+    ctx.save_for_backward(x, res, gamma)
+    ctx.eps = eps
+
+
+def _ln_backward(ctx, g):
+    x, res, gamma = ctx.saved_tensors
+    x = _f32c(x, "x")
+    res = None if res is None else _f32c(res, "res")
+    gamma = _f32c(gamma, "gamma")
+    g = _f32c(g, "grad")
+    D = x.shape[-1]
+    gz = torch.empty_like(x)
+    gg = torch.zeros_like(gamma)
+    gb = torch.zeros_like(gamma)
+    _check(_lib.mgnns_add_layernorm_bwd(x.data_ptr(), _ptr(res), gamma.data_ptr(), g.data_ptr(), x.numel() // D, D,
+                                        float(ctx.eps), gz.data_ptr(), gg.data_ptr(), gb.data_ptr(), _stream()),
+           "add_layernorm_bwd")
+    return gz, (gz if res is not None else None), gg, gb, None
+
+
+torch.library.register_autograd("mgnns::add_layernorm", _ln_backward, setup_context=_ln_setup)
+
+
+# ----------------------------------------------------------------------------- image bank (+ global max pool)
+_LIB.define("imgbank(Tensor fmap, Tensor weight, Tensor bias) -> (Tensor, Tensor, Tensor)")
+
+
+def _imgbank_check(fmap, weight, bias):
+    _need_cuda(fmap, weight, bias)
+    fmap = _f32c(fmap, "fmap")
+    weight = _f32c(weight, "weight")
+    bias = _f32c(bias, "bias")
+    if fmap.dim() == 4:
+        fmap = fmap.reshape(fmap.shape[0], fmap.shape[1], -1)
+    if fmap.dim() != 3 or weight.dim() != 2 or weight.shape[1] != fmap.shape[1] or bias.numel() != weight.shape[0]:
+        raise RuntimeError("mgnns::imgbank: expected fmap [B,C,H,W], weight [O,C], bias [O]")
+    return fmap, weight, bias
+
+
+def _imgbank_impl(fmap, weight, bias):
+    fmap, weight, bias = _imgbank_check(fmap, weight, bias)
+    B, C, P = fmap.shape
+    O = weight.shape[0]
+    bank = torch.empty((B, P, O), device=fmap.device, dtype=torch.float32)
+    pooled = torch.empty((B, C), device=fmap.device, dtype=torch.float32)
+    argmax = torch.empty((B, C), device=fmap.device, dtype=torch.int32)
+    s = _stream()
+    _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
+    # bank_b [P,O] = fmap_b^T [P,C] @ weight^T [C,O] + bias
+    for b0 in range(0, B, 65535):
+        nb = min(65535, B - b0)
+        gemm_raw(1, 1, P, O, C, (fmap, b0 * C * P), P, C * P, weight, C, 0, (bank, b0 * P * O), O, P * O,
+                 batch=nb, bias=bias)
+    return bank, pooled, argmax
+
+
+def _imgbank_fake(fmap, weight, bias):
+    B, C = fmap.shape[0], fmap.shape[1]
+    P = fmap.numel() // (B * C)
+    return (fmap.new_empty((B, P, weight.shape[0])), fmap.new_empty((B, C)),
+            fmap.new_empty((B, C), dtype=torch.int32))
+
+
+_LIB.impl("imgbank", _imgbank_impl, "CUDA")
+torch.library.register_fake("mgnns::imgbank", _imgbank_fake)
+
+
+def _imgbank_setup(ctx, inputs, output):
+    fmap, weight, bias = inputs
+    ctx.save_for_backward(fmap, weight, output[2])
+    ctx.fshape = fmap.shape
+
+
+def _pick_reduce(batch, target=32):
+    r = min(target, batch)
+    while batch % r:
+        r -= 1
+    return r
+
+
+def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
+    fmap, weight, argmax = ctx.saved_tensors
+    fmap3, weight, _ = _imgbank_check(fmap, weight, weight.new_empty((weight.shape[0],)))
+    B, C, P = fmap3.shape
+    O = weight.shape[0]
+    g_f = g_w = g_b = None
+    if g_bank is not None:
+        g_bank = _f32c(g_bank, "grad_bank")
+    if ctx.needs_input_grad[1] and g_bank is not None:
+        # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
+        g_w = torch.zeros_like(weight)
+        r = _pick_reduce(B)
+        gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, g_w, C, 0, batch=B, reduce=r, accumulate=1)
+    if ctx.needs_input_grad[2] and g_bank is not None:
+        g_b = colsum(g_bank.reshape(B * P, O))
+    if ctx.needs_input_grad[0]:
+        g_f = torch.empty_like(fmap3) if g_bank is not None else torch.zeros_like(fmap3)
+        if g_bank is not None:
+            # gF_b [C,P] = weight^T [C,O] @ gbank_b^T [O,P]
+            for b0 in range(0, B, 65535):
+                nb = min(65535, B - b0)
+                gemm_raw(1, 1, C, P, O, weight, C, 0, (g_bank, b0 * P * O), O, P * O, (g_f, b0 * C * P), P, C * P,
+                         batch=nb)
+        if g_pooled is not None:
+            g_pooled = _f32c(g_pooled, "grad_pooled")
+            _check(_lib.mgnns_rowmax_bwd_f32(g_pooled.data_ptr(), argmax.data_ptr(), B * C, P, g_f.data_ptr(),
+                                             _stream()), "rowmax_bwd")
+        g_f = g_f.reshape(ctx.fshape)
+    return g_f, g_w, g_b
+
+
+torch.library.register_autograd("mgnns::imgbank", _imgbank_backward, setup_context=_imgbank_setup)
+
+
+# ----------------------------------------------------------------------------- PMI counting (no autograd)
+def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count: int):
+    """tokens int32 [D,L] on CUDA -> (rowptr int32[V+1], col int32[nnz], cnt int32[nnz], word_count int64[V]).
+
+    Dense int32 [V,V] table in HBM (1.6 GB at V=20k, 10 GB at V=50k of the 180 GB), integer atomics,
+    then an ordered compaction to CSR keeping cells >= min_count.
+    """
+    _need_cuda(tokens)
+    if tokens.dtype != torch.int32 or tokens.dim() != 2:
+        raise RuntimeError("mgnns pmi_count: tokens must be int32 [D,L]")
+    tokens = tokens.contiguous()
+    Dn, L = tokens.shape
+    dev = tokens.device
+    if V * V * 4 > 120 * (1 << 30):
+        raise RuntimeError("mgnns pmi_count: V=%d needs a %.0f GB count table" % (V, V * V * 4 / 2**30))
+    pair = torch.zeros((V, V), device=dev, dtype=torch.int32)
+    wc = torch.zeros((V,), device=dev, dtype=torch.int64)
+    s = _stream()
+    _check(_lib.mgnns_pmi_count(tokens.data_ptr(), Dn, L, V, window, pad_id, pair.data_ptr(), wc.data_ptr(), s),
+           "pmi_count")
+    nnz_row = torch.empty((V,), device=dev, dtype=torch.int32)
+    rowptr = torch.empty((V + 1,), device=dev, dtype=torch.int32)
+    _check(_lib.mgnns_count_row_nnz_i32(pair.data_ptr(), V, V, min_count, nnz_row.data_ptr(), s), "count_row_nnz")
+    _check(_lib.mgnns_exclusive_scan_i32(nnz_row.data_ptr(), rowptr.data_ptr(), V, s), "scan")
+    nnz = int(rowptr[-1].item())
+    col = torch.empty((max(nnz, 1),), device=dev, dtype=torch.int32)[:nnz]
+    cnt = torch.empty((max(nnz, 1),), device=dev, dtype=torch.int32)[:nnz]
+    _check(_lib.mgnns_count_fill_csr_i32(pair.data_ptr(), V, V, min_count, rowptr.data_ptr(), col.data_ptr(),
+                                         cnt.data_ptr(), s), "count_fill_csr")
+    return rowptr, col, cnt, wc
