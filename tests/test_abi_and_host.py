@@ -1,0 +1,149 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares; host-side logic
+(adjacency builders, PMI float stage, edge map, module construction/state_dict contract)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mgnns_test_helpers as H
+from mgnns_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, 'include', 'mgnns_b200.h')) as f:
+        src = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(mgnns_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mgnns_b200 import _abi
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), 'missing export: ' + n
+        assert n in _abi.SIGNATURES or n in _abi.OPTIONAL_SIGNATURES, 'no ctypes binding for ' + n
+    assert lib.mgnns_abi_version() == 1
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'mgnns_b200')):
+        for fn in files:
+            if fn.endswith('.py'):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
+
+
+def test_ops_reject_cpu_tensors():
+    from mgnns_b200 import ops  # noqa: F401
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.mgnns.mm(torch.randn(2, 2), torch.randn(2, 2), None, False, False, 0, 0.0)
+
+
+def test_gen_A_gen_adj_api_bit_exact_vs_reference(golden):
+    from mgnns_b200.api.graph_util import gen_A, gen_adj
+    z = golden('adj.npz')
+    for kind, n, ts in (('object', 80, (0.3, 0.4, 0.6)), ('place', 365, (0.3, 0.5))):
+        for t in ts:
+            tag = '%s_t%02d' % (kind, int(t * 10))
+            A, nums = gen_A(n, t, synth.adj_dict(kind))
+            ref = np.zeros((n, n))
+            ref[z[tag + '_A_rows'], z[tag + '_A_cols']] = z[tag + '_A_vals']
+            assert np.array_equal(A, ref) and nums.shape == (n, 1)
+            adj = gen_adj(torch.from_numpy(A).float()).numpy()
+            refadj = np.zeros((n, n), dtype=np.float32)
+            refadj[z[tag + '_adj_rows'], z[tag + '_adj_cols']] = z[tag + '_adj_vals']
+            assert np.array_equal(adj, refadj)
+
+
+def test_sparse_edge_map_lookup_and_roundtrip():
+    from mgnns_b200.api.pmi import SparseEdgeMap
+    rs = np.random.RandomState(0)
+    dense = np.zeros((40, 40), dtype=np.int64)
+    idx = rs.choice(1600, 200, replace=False)
+    dense.flat[np.sort(idx)] = np.arange(1, 201)
+    m = SparseEdgeMap.from_dense(dense)
+    assert np.array_equal(m.toarray(), dense)
+    for i, j in rs.randint(0, 40, (300, 2)):
+        assert m[i, j] == dense[i, j]
+    implicit = SparseEdgeMap(m.rowptr, m.col, 40)          # ids = 1 + CSR position
+    assert np.array_equal(implicit.toarray(), dense)
+
+
+def test_pmi_host_stage_matches_reference(golden):
+    """Host float64 stage (pmi_from_counts) fed with oracle integer counts reproduces the reference's
+    edge set, ids and weights on real text."""
+    from mgnns_b200.api import pmi
+    from oracle import pmi_oracle as PO
+    z = golden('pmi_val400.npz')
+    texts, vocab = list(z['texts']), list(z['vocab'])
+    ids, pad_id = pmi.encode_corpus(texts, vocab)
+    ids_o, pad_o = PO.encode(texts, vocab)
+    assert np.array_equal(ids, ids_o) and pad_id == pad_o == 0
+    pair, wc = PO.counts_numpy(ids, pad_id, len(vocab), int(z['window']))
+    pair[pair < int(z['min_cooc'])] = 0
+    rows, cols = np.nonzero(pair)
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=len(vocab)))])
+    keep, vals = pmi.pmi_from_counts(rowptr, cols, pair[rows, cols], wc)
+    assert np.array_equal(rows[keep], z['rows']) and np.array_equal(cols[keep], z['cols'])
+    np.testing.assert_allclose(vals[keep].astype(np.float32), z['weights'][1:, 0], rtol=1e-6)
+
+
+def test_text_padding_drops_long_texts():
+    from mgnns_b200.api import pmi
+    texts = ['a b', ' '.join(['x'] * 99), ' '.join(['x'] * 100), 'a  b']
+    padded = pmi.text_padding(texts)
+    assert len(padded) == 3 and all(len(p) == 100 for p in padded)
+    assert padded[2][:3] == ['a', '', 'b']
+
+
+def _build_cpu_model(cfg):
+    from mgnns_b200.api.multi_gcn import IdentityTrunk, Multi_GCN_Multihead_Att
+    from mgnns_b200.api.text_gcn import Model as TextModel
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=1, docs=200)
+    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, cfg['V'])]
+    tm = TextModel(7, 300, vocab, cfg['ngram'], 0.5, count, emap, pmi=torch.zeros(count, 1))
+    opt = dict(emb_path='', bidirectional=True, hidden_size=150, emb_size=300, num_layers=2, dropout=0.5,
+               emb_type='random', vocab_size=cfg['V'], stack_num=2, n_head=4, d_kv=128, is_regu=False)
+    torch.manual_seed(0)
+    return Multi_GCN_Multihead_Att(opt, 7, tm, IdentityTrunk(), IdentityTrunk(), 80, 365, object_t=0.4, place_t=0.3,
+                                   in_channel=300, object_adj_file=synth.adj_dict('object'),
+                                   place_adj_file=synth.adj_dict('place')), count
+
+
+def test_state_dict_contract_and_reference_initialisation(golden):
+    """Same parameter names/shapes as the reference and — because modules are constructed in the
+    reference's order with its initialisers — identical values under torch.manual_seed(0)."""
+    z = golden('model_init_seed0.npz')
+    model, count = _build_cpu_model(H.MODEL_CFG)
+    sd = model.state_dict()
+    ref_names = set(z.files)
+    mine = {n for n in sd if not n.startswith('text_features.')}
+    assert mine == ref_names, (sorted(mine - ref_names)[:5], sorted(ref_names - mine)[:5])
+    for n in sorted(ref_names):
+        stat = z[n]
+        assert tuple(int(v) for v in stat[2:]) == tuple(sd[n].shape), n
+        np.testing.assert_allclose([sd[n].double().sum().item(), sd[n].double().abs().sum().item()], stat[:2],
+                                   rtol=1e-9, atol=1e-9, err_msg=n)
+    for n, shape in H.state_shapes(H.MODEL_CFG, count).items():
+        assert tuple(sd[n].shape) == tuple(shape), n
+
+
+def test_optimizer_groups_omit_the_never_stepped_parameters():
+    model, _ = _build_cpu_model(H.MODEL_CFG)
+    groups = model.get_config_optim(1e-4, 0.1)
+    assert len(groups) == 12
+    stepped = {id(p) for g in groups for p in g['params']}
+    named = dict(model.named_parameters())
+    for n in ('multi_linear_1.weight', 'multi_linear_2.weight', 'liner_img_object.weight', 'object_linear_5.weight',
+              'place_x_linear.weight', 'embedding.weight', 'object_A'):
+        assert id(named[n]) not in stepped, n
+    for n in ('gc1.weight', 'lstm.weight_ih_l0', 'text_features.node_hidden.weight',
+              'img_object_text_multi_head_att.0.slf_attn.w_qs.weight', 'object_attention.w_q.weight'):
+        assert id(named[n]) in stepped, n

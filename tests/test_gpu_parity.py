@@ -1,0 +1,563 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden
+vectors produced by the reference's own code.
+
+Tolerances (fp32 mode, stated per BASELINE.json north_star): logits 1e-3 relative / 1e-4 absolute,
+argmax identical, integer counts / edge ids bit-exact.  Kernel-level checks use tighter bounds.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mgnns_test_helpers as H
+from mgnns_b200 import synth
+from oracle import mgnns_oracle as O
+from oracle import pmi_oracle as PO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device('cuda', 0)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mgnns_b200 import ops as _ops
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(a, b, rtol=1e-4, atol=1e-5, msg=''):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=msg)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(37, 301, 77), (128, 128, 64), (1, 7, 300), (513, 300, 2048), (300, 100, 5)])
+def test_gemm_all_layouts(ops, dev, ta, tb, M, N, K):
+    a = rnd(K, M, seed=1) if ta else rnd(M, K, seed=1)
+    b = rnd(N, K, seed=2) if tb else rnd(K, N, seed=2)
+    bias = rnd(N, seed=3)
+    ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + bias.double()
+    out = torch.ops.mgnns.mm(a.to(dev), b.to(dev), bias.to(dev), bool(ta), bool(tb), ops.ACT_NONE, 0.0)
+    close(out, ref, rtol=2e-5, atol=2e-5 * math.sqrt(K))
+    out = torch.ops.mgnns.mm(a.to(dev), b.to(dev), bias.to(dev), bool(ta), bool(tb), ops.ACT_LEAKY, 0.2)
+    close(out, torch.nn.functional.leaky_relu(ref, 0.2), rtol=2e-5, atol=2e-5 * math.sqrt(K))
+
+
+def test_gemm_strided_rows_and_autograd(ops, dev):
+    big = rnd(64, 200, seed=4).to(dev)
+    a = big[:, 3:80].detach().requires_grad_()        # row stride 200, unaligned start
+    w = rnd(50, 77, seed=5).to(dev).requires_grad_()
+    bias = rnd(50, seed=6).to(dev).requires_grad_()
+    y = ops.linear(a, w, bias, ops.ACT_RELU)
+    r = rnd(64, 50, seed=7).to(dev)
+    (y * r).sum().backward()
+    ac, wc, bc = a.detach().cpu().double().requires_grad_(), w.detach().cpu().double().requires_grad_(), \
+        bias.detach().cpu().double().requires_grad_()
+    yr = torch.relu(ac @ wc.t() + bc)
+    (yr * r.cpu().double()).sum().backward()
+    close(y, yr, 1e-5, 1e-5)
+    close(a.grad, ac.grad, 1e-4, 1e-5)
+    close(w.grad, wc.grad, 1e-4, 1e-5)
+    close(bias.grad, bc.grad, 1e-4, 1e-5)
+
+
+def test_gemm_batch_reduce_accumulate(ops, dev):
+    B, M, N, K = 12, 33, 70, 19
+    a, b = rnd(B, M, K, seed=8), rnd(B, K, N, seed=9)
+    c = torch.zeros(3, M, N, device=dev)
+    ops.gemm_raw(0, 0, M, N, K, a.to(dev), K, M * K, b.to(dev), N, K * N, c, N, M * N, batch=B, reduce=4)
+    ref = torch.bmm(a.double(), b.double()).view(3, 4, M, N).sum(1)
+    close(c, ref, 1e-5, 1e-4)
+    c2 = torch.ones(M, N, device=dev)
+    ops.gemm_raw(0, 0, M, N, K, a.to(dev), K, M * K, b.to(dev), N, K * N, c2, N, 0, batch=B, reduce=3, accumulate=1)
+    close(c2, 1 + torch.bmm(a.double(), b.double()).sum(0), 1e-5, 1e-4)
+
+
+def test_head_mm_fwd_bwd(ops, dev):
+    B, Hh, dk, D = 9, 4, 128, 300
+    x = rnd(B, Hh * dk, seed=10).to(dev).requires_grad_()
+    w = rnd(Hh * dk, D, seed=11, scale=0.1).to(dev).requires_grad_()
+    u = torch.ops.mgnns.head_mm(x, w, Hh, 0)
+    r = rnd(B, Hh * D, seed=12).to(dev)
+    (u * r).sum().backward()
+    xc, wc = x.detach().cpu().double().requires_grad_(), w.detach().cpu().double().requires_grad_()
+    ur = torch.einsum('bhk,hkd->bhd', xc.view(B, Hh, dk), wc.view(Hh, dk, D)).reshape(B, Hh * D)
+    (ur * r.cpu().double()).sum().backward()
+    close(u, ur, 1e-5, 1e-4)
+    close(x.grad, xc.grad, 1e-4, 1e-4)
+    close(w.grad, wc.grad, 1e-4, 1e-4)
+    c = rnd(B, Hh * D, seed=13).to(dev).requires_grad_()
+    w2 = rnd(Hh * dk, D, seed=14, scale=0.1).to(dev).requires_grad_()
+    o = torch.ops.mgnns.head_mm(c, w2, Hh, 1)
+    r2 = rnd(B, Hh * dk, seed=15).to(dev)
+    (o * r2).sum().backward()
+    cc, w2c = c.detach().cpu().double().requires_grad_(), w2.detach().cpu().double().requires_grad_()
+    orf = torch.einsum('bhd,hkd->bhk', cc.view(B, Hh, D), w2c.view(Hh, dk, D)).reshape(B, Hh * dk)
+    (orf * r2.cpu().double()).sum().backward()
+    close(o, orf, 1e-5, 1e-4)
+    close(c.grad, cc.grad, 1e-4, 1e-4)
+    close(w2.grad, w2c.grad, 1e-4, 1e-4)
+
+
+# ------------------------------------------------------------------------------------------- SpMM / CSR
+def random_adj(n, m, density, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.rand(n, m, generator=g)
+    v = torch.randn(n, m, generator=g)
+    return torch.where(a < density, v, torch.zeros(()))
+
+
+@pytest.mark.parametrize("n,F,batch", [(80, 300, 0), (365, 1024, 0), (200, 7, 3), (1500, 300, 5), (64, 2048, 2)])
+def test_spmm_matches_dense(dev, n, F, batch):
+    from mgnns_b200.api.graph_util import CSRAdjacency
+    adj = random_adj(n, n, 0.05, seed=n)
+    adj[3] = 0           # an empty row
+    x = rnd(*( (batch, n, F) if batch else (n, F)), seed=F)
+    csr = CSRAdjacency.from_dense(adj.to(dev))
+    assert csr.nnz == int((adj != 0).sum())
+    xg = x.to(dev).requires_grad_()
+    y = csr.spmm(xg)
+    ref = torch.matmul(adj.double(), x.double())
+    close(y, ref, 1e-5, 1e-5)
+    r = rnd(*y.shape, seed=1)
+    (y * r.to(dev)).sum().backward()
+    close(xg.grad, torch.matmul(adj.double().t(), r.double()), 1e-5, 1e-5)
+
+
+def test_dense_to_csr_ordering_and_scan(ops, dev):
+    adj = random_adj(3000, 517, 0.02, seed=5)
+    rowptr, col, val = ops.dense_to_csr(adj.to(dev))
+    rows, cols = np.nonzero(adj.numpy())
+    assert np.array_equal(col.cpu().numpy(), cols)
+    assert np.array_equal(val.cpu().numpy(), adj.numpy()[rows, cols])
+    ref_ptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=3000))])
+    assert np.array_equal(rowptr.cpu().numpy(), ref_ptr)
+
+
+def test_graph_convolution_matches_reference_golden(dev, golden):
+    from mgnns_b200.api.graph_util import gen_A, gen_adj
+    from mgnns_b200.api.multi_gcn import GraphConvolution
+    z = golden('modules.npz')
+    lg = synth.label_graphs()
+    A, _ = gen_A(80, 0.4, synth.adj_dict('object'))
+    adj = gen_adj(torch.from_numpy(A).float().to(dev))
+    gc = GraphConvolution(300, 64)
+    synth.fill_parameters(gc, seed=3)
+    gc.to(dev)
+    out = gc(torch.from_numpy(lg['object_glove']).float().to(dev), adj)
+    close(out, z['gc_out'], 1e-4, 1e-5)
+    gcb = GraphConvolution(300, 32, bias=True)
+    synth.fill_parameters(gcb, seed=4)
+    gcb.to(dev)
+    out = gcb(torch.from_numpy(z['gcb_x']).to(dev), adj)
+    close(out, z['gcb_out'], 1e-4, 1e-5)
+    # out_features < in_features takes the other association order
+    gcs = GraphConvolution(300, 16)
+    synth.fill_parameters(gcs, seed=6)
+    x = torch.from_numpy(lg['object_glove']).float()
+    ref = O.graph_convolution(x, adj.cpu(), gcs.weight.detach())
+    close(gcs.to(dev)(x.to(dev), adj), ref, 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------- text GCN
+def _text_case(V, B, L, ngram, seed, dev, extra_docs=()):
+    text, lens, _ = synth.make_texts(B, V, L, seed=seed)
+    for i, d in enumerate(extra_docs):
+        text[i] = torch.tensor(d + [0] * (L - len(d)))
+    emap, count = synth.synthetic_edge_map(V, seed=seed, docs=400)
+    h = rnd(V, 300, seed=seed + 1, scale=0.4)
+    w = 1.0 + 0.3 * rnd(count, 1, seed=seed + 2)
+    return text, emap, count, h, w
+
+
+@pytest.mark.parametrize("ngram", [1, 4, 5])
+def test_text_maxagg_forward_backward_vs_oracle(dev, ngram):
+    V, B, L = 200, 12, 100
+    extra = [[0] * 0,                                # all PAD
+             [5, 0, 0, 7, 5, 0, 9],                  # interior PADs, duplicates
+             [3],                                    # single token
+             list(range(2, 102)),                    # full length, all distinct
+             [4] * 100]                              # full length, one word
+    text, emap, count, h, w = _text_case(V, B, L, ngram, 3, dev, extra)
+    text[0] = 0
+    hc, wc = h.clone().requires_grad_(), w.clone().requires_grad_()
+    ref = O.text_gcn_forward(text, hc, wc, lambda u, v: emap[u, v], ngram)
+    r = rnd(B, 300, seed=9)
+    (ref * r).sum().backward()
+    hg, wg = h.to(dev).requires_grad_(), w.to(dev).requires_grad_()
+    rp = torch.from_numpy(emap.rowptr.astype(np.int32)).to(dev)
+    cl = torch.from_numpy(emap.col.astype(np.int32)).to(dev)
+    out = torch.ops.mgnns.text_maxagg(text.to(dev), hg, wg, rp, cl, None, ngram, 100, True)
+    close(out, ref, 1e-5, 1e-5)
+    (out * r.to(dev)).sum().backward()
+    close(hg.grad, hc.grad, 1e-4, 1e-5)
+    close(wg.grad, wc.grad, 1e-4, 1e-5)
+
+
+def test_text_gcn_module_truncation_and_explicit_eids(dev):
+    from mgnns_b200.api.pmi import SparseEdgeMap
+    from mgnns_b200.api.text_gcn import Model
+    V, B, L = 150, 8, 120            # longer than max_length -> truncated to 100
+    text, _, _ = synth.make_texts(B, V, L, seed=21)
+    text[0, :] = torch.arange(2, 122) % (V - 2) + 2
+    emap, count = synth.synthetic_edge_map(V, seed=21, docs=300)
+    dense = emap.toarray()
+    perm = np.random.RandomState(0).permutation(count - 1) + 1       # arbitrary (non row-major) ids
+    dense[dense > 0] = perm[dense[dense > 0] - 1]
+    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, V)]
+    m = Model(7, 300, vocab, 4, 0.5, count, dense, pmi=torch.zeros(count, 1))
+    synth.fill_parameters(m, seed=2)
+    m.eval().to(dev)
+    ref = O.text_gcn_forward(text, m.node_hidden.weight.detach().cpu(), m.seq_edge_w.weight.detach().cpu(),
+                             lambda u, v: int(dense[u, v]), 4, max_length=100)
+    close(m(text.to(dev)), ref, 1e-5, 1e-5)
+    # train mode: dropout(0.5) then ReLU == ReLU then dropout; keep-rate and scaling
+    m.train()
+    torch.manual_seed(0)
+    y = m(text.to(dev))
+    nz = ref > 0
+    kept = (y.cpu() != 0) & nz
+    assert 0.4 < kept.sum().item() / nz.sum().item() < 0.6
+    close(y.cpu()[kept], 2 * ref[kept], 1e-5, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------- attention layers
+def test_layernorm_fwd_bwd(dev, golden):
+    from mgnns_b200.api.layers import LayerNorm
+    z = golden('modules.npz')
+    ln = LayerNorm(300)
+    synth.fill_parameters(ln, seed=1)
+    ln.to(dev)
+    close(ln(torch.from_numpy(z['ln_x']).to(dev)), z['ln_y'], 1e-5, 1e-5)
+    for D, rows in ((300, 37), (64, 5), (1000, 3)):
+        x, res = rnd(rows, D, seed=D), rnd(rows, D, seed=D + 1)
+        gam, bet = 1 + 0.1 * rnd(D, seed=2), 0.1 * rnd(D, seed=3)
+        r = rnd(rows, D, seed=4)
+        leaves = [t.clone().double().requires_grad_() for t in (x, res, gam, bet)]
+        (O.layer_norm(leaves[0] + leaves[1], leaves[2], leaves[3]) * r.double()).sum().backward()
+        gl = [t.to(dev).requires_grad_() for t in (x, res, gam, bet)]
+        y = torch.ops.mgnns.add_layernorm(gl[0], gl[1], gl[2], gl[3], 1e-6)
+        close(y, O.layer_norm(x.double() + res.double(), gam.double(), bet.double()), 1e-5, 1e-5)
+        (y * r.to(dev)).sum().backward()
+        for a, b, nm in zip(gl, leaves, 'x res gamma beta'.split()):
+            close(a.grad, b.grad, 2e-4, 2e-5, msg='%s D=%d' % (nm, D))
+
+
+def _mha_layer(dev, seed=2, dropout=0.5):
+    from mgnns_b200.api.layers import MyMultiHeadAttention
+    layer = MyMultiHeadAttention(4, 300, 128, dropout=dropout, need_mask=False)
+    synth.fill_parameters(layer, seed=seed)
+    return layer.to(dev)
+
+
+def test_mha_layer_matches_reference_golden(dev, golden):
+    z = golden('modules.npz')
+    layer = _mha_layer(dev).eval()
+    q = torch.from_numpy(z['mha_q']).to(dev).requires_grad_()
+    bank = torch.from_numpy(z['mha_bank']).to(dev).requires_grad_()
+    mask = torch.from_numpy(z['mha_mask']).to(dev)
+    y, attn = layer(q, bank, bank, mask)
+    close(y, z['mha_out_masked'], 1e-4, 1e-4)
+    assert attn.shape == z['mha_attn_masked'].shape
+    close(attn, z['mha_attn_masked'], 1e-4, 1e-6)
+    yu, attnu = layer(q, bank, bank, None)
+    close(yu, z['mha_out_unmasked'], 1e-4, 1e-4)
+    close(attnu, z['mha_attn_unmasked'], 1e-4, 1e-6)
+    (y * torch.from_numpy(z['mha_r']).to(dev)).sum().backward()
+    close(q.grad, z['mha_gq'], 1e-3, 1e-4)
+    close(bank.grad, z['mha_gbank'], 1e-3, 1e-5)
+    for n, p in layer.named_parameters():
+        g = z['mha_g_' + n]
+        if n == 'slf_attn.w_ks.bias':
+            # the key bias shifts every score of a head equally; softmax cancels it (gradient == 0 up to
+            # rounding in the reference, exactly absent here)
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-6
+            assert float(np.abs(g).max()) < 1e-5
+            continue
+        if g.ndim == 0:
+            np.testing.assert_allclose(p.grad.norm().item(), float(g), rtol=1e-3, err_msg=n)
+        else:
+            close(p.grad, g, 1e-3, 1e-5, msg=n)
+
+
+@pytest.mark.parametrize("B,L,Hh,masked", [(7, 196, 4, False), (5, 100, 4, True), (3, 33, 16, True), (2, 1, 4, False)])
+def test_attn_q1_core_vs_dense_formula(dev, B, L, Hh, masked):
+    D = 300
+    u, bank = rnd(B, Hh, D, seed=1, scale=0.2), rnd(B, L, D, seed=2)
+    mask = None
+    if masked:
+        lens = torch.randint(1, L + 1, (B,), generator=torch.Generator().manual_seed(3))
+        mask = (torch.arange(L).unsqueeze(0) < lens.unsqueeze(1)).float()
+    scale = 1 / math.sqrt(128)
+    ud, bd = u.double().requires_grad_(), bank.double().requires_grad_()
+    s = torch.einsum('bhd,bld->bhl', ud, bd) * scale
+    if mask is not None:
+        s = s.masked_fill(mask.unsqueeze(1) == 0, float('-inf'))
+    p = torch.softmax(s, -1)
+    ctx_ref = torch.einsum('bhl,bld->bhd', p, bd)
+    r, r2 = rnd(B, Hh, D, seed=4).double(), rnd(B, Hh, seed=5).double()
+    ((ctx_ref * r).sum() + (p.sum(-1) * r2).sum()).backward()
+    ug, bg = u.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
+    ctx, attn, psum, lse = torch.ops.mgnns.attn_q1(ug, bg, None if mask is None else mask.to(dev), scale, 0.0, 0)
+    close(ctx, ctx_ref, 1e-4, 1e-5)
+    close(attn.view(Hh, B, L).permute(1, 0, 2), p, 1e-4, 1e-6)
+    close(psum, torch.ones(B, Hh), 1e-5, 1e-5)
+    close(lse, torch.logsumexp(s, -1), 1e-5, 1e-5)
+    ((ctx * r.float().to(dev)).sum() + (psum * r2.float().to(dev)).sum()).backward()
+    close(ug.grad, ud.grad, 1e-3, 1e-5)
+    close(bg.grad, bd.grad, 1e-3, 1e-5)
+
+
+def test_attention_dropout_statistics_and_determinism(dev):
+    B, L, Hh, D = 64, 100, 4, 300
+    u, bank = rnd(B, Hh, D, seed=1, scale=0.05).to(dev), rnd(B, L, D, seed=2).to(dev)
+    _, attn0, _, _ = torch.ops.mgnns.attn_q1(u, bank, None, 0.1, 0.0, 0)
+    ctx1, attn1, psum1, _ = torch.ops.mgnns.attn_q1(u, bank, None, 0.1, 0.1, 1234)
+    ctx2, attn2, _, _ = torch.ops.mgnns.attn_q1(u, bank, None, 0.1, 0.1, 1234)
+    _, attn3, _, _ = torch.ops.mgnns.attn_q1(u, bank, None, 0.1, 0.1, 99)
+    assert torch.equal(attn1, attn2) and torch.equal(ctx1, ctx2)
+    assert not torch.equal(attn1, attn3)
+    kept = attn1 != 0
+    assert abs(kept.float().mean().item() - 0.9) < 0.01
+    close(attn1[kept], attn0[kept] / 0.9, 1e-5, 1e-7)
+    close(psum1, attn1.view(Hh, B, L).sum(-1).t(), 1e-5, 1e-6)
+    close(ctx1, torch.einsum('hbl,bld->bhd', attn1.view(Hh, B, L), bank), 1e-4, 1e-5)
+    # backward regenerates the same mask: finite-difference-free check against autograd on the dense formula
+    ug, bg = u.clone().requires_grad_(), bank.clone().requires_grad_()
+    ctx, _, psum, _ = torch.ops.mgnns.attn_q1(ug, bg, None, 0.1, 0.1, 1234)
+    r = rnd(B, Hh, D, seed=7).to(dev)
+    ((ctx * r).sum() + psum.sum()).backward()
+    ud, bd = u.double().requires_grad_(), bank.double().requires_grad_()
+    p = torch.softmax(torch.einsum('bhd,bld->bhl', ud, bd) * 0.1, -1)
+    pt = p * (kept.view(Hh, B, L).permute(1, 0, 2).double() / 0.9)
+    ((torch.einsum('bhl,bld->bhd', pt, bd) * r.double()).sum() + pt.sum()).backward()
+    close(ug.grad, ud.grad, 1e-3, 1e-5)
+    close(bg.grad, bd.grad, 1e-3, 1e-5)
+
+
+def test_label_attention_matches_reference_golden_and_grads(dev, golden):
+    from mgnns_b200.api.multi_gcn import Attention
+    z = golden('modules.npz')
+    lg = synth.label_graphs()
+    att = Attention(hid_dim=300, image_dim=80, n_heads=5, dropout=0.5)
+    synth.fill_parameters(att, seed=5)
+    att.eval().to(dev)
+    key = torch.from_numpy(z['latt_key']).to(dev).requires_grad_()
+    query = torch.from_numpy(lg['label_glove'])
+    out = att(query, key, key)
+    close(out, z['latt_out'], 1e-4, 1e-5)
+    r = rnd(*out.shape, seed=3)
+    (out * r.to(dev)).sum().backward()
+    P = {n: p.detach().cpu().double().requires_grad_() for n, p in att.named_parameters()}
+    kc = torch.from_numpy(z['latt_key']).double().requires_grad_()
+    (O.label_attention(P, '', query.double(), kc, kc, 5) * r.double()).sum().backward()
+    close(key.grad, kc.grad, 1e-3, 1e-6)
+    for n, p in att.named_parameters():
+        close(p.grad, P[n].grad, 1e-3, 1e-5, msg=n)
+    # dropout on the softmax probabilities (train mode): determinism + keep rate
+    att.train()
+    torch.manual_seed(5)
+    o1 = att(query, key.detach(), key.detach())
+    torch.manual_seed(5)
+    o2 = att(query, key.detach(), key.detach())
+    assert torch.equal(o1, o2)
+
+
+# ------------------------------------------------------------------------------------------- image bank
+def test_imgbank_fwd_bwd(dev):
+    B, C, P_, Oo = 5, 2048, 196, 300
+    f = torch.relu(rnd(B, C, 14, 14, seed=1))
+    f[0, 7] = 0                                  # an all-zero channel: arg-max must be position 0
+    w, b = rnd(Oo, C, seed=2, scale=0.02), rnd(Oo, seed=3)
+    fg, wg, bg = f.to(dev).requires_grad_(), w.to(dev).requires_grad_(), b.to(dev).requires_grad_()
+    bank, pooled, argmax = torch.ops.mgnns.imgbank(fg, wg, bg)
+    fd, wd, bd = f.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    bank_ref = torch.nn.functional.linear(fd.view(B, C, -1).permute(0, 2, 1), wd, bd)
+    pooled_ref = torch.nn.functional.max_pool2d(fd, 14, 14).view(B, C)
+    close(bank, bank_ref, 1e-4, 1e-4)
+    assert torch.equal(pooled.cpu(), pooled_ref.float())
+    assert int(argmax[0, 7]) == 0
+    r1, r2 = rnd(B, P_, Oo, seed=4), rnd(B, C, seed=5)
+    ((bank * r1.to(dev)).sum() + (pooled * r2.to(dev)).sum()).backward()
+    ((bank_ref * r1.double()).sum() + (pooled_ref * r2.double()).sum()).backward()
+    close(wg.grad, wd.grad, 1e-4, 1e-3)
+    close(bg.grad, bd.grad, 1e-4, 1e-3)
+    close(fg.grad, fd.grad, 1e-4, 1e-4)
+
+
+# ------------------------------------------------------------------------------------------- PMI
+KAT_VOCAB = ['PAD', 'UNK', 'a', 'b', 'c', 'd', 'e']
+KAT_DOCS = ["a b c a d", "b c d e", "a a b zzz c", "e d c b a b c"]
+
+
+def test_pmi_counts_bit_exact_kat(dev, golden):
+    from mgnns_b200.api import pmi
+    z = golden('pmi_kat.npz')
+    for tag, mc in (('w2m1', 1), ('w2m2', 2)):
+        w, emap, count = pmi.cal_PMI_from_texts(KAT_DOCS, KAT_VOCAB, 2, mc, device=dev)
+        assert count == int(z['kat_%s_count' % tag])
+        assert np.array_equal(emap.toarray(), z['kat_%s_map' % tag])
+        np.testing.assert_allclose(w.numpy(), z['kat_%s_weights' % tag], rtol=1e-6)
+    pair, wc = PO.counts_loops(KAT_DOCS, KAT_VOCAB, 2)
+    _, emap, _ = pmi.cal_PMI_from_texts(KAT_DOCS, KAT_VOCAB, 2, 1, device=dev)
+    rowptr, col, cnt = emap.pair_counts
+    dense = np.zeros_like(pair)
+    dense[np.repeat(np.arange(7), np.diff(rowptr)), col] = cnt
+    assert np.array_equal(dense, pair) and np.array_equal(emap.word_count, wc)
+
+
+def test_pmi_real_text_bit_exact_vs_reference(dev, golden):
+    from mgnns_b200.api import pmi
+    z = golden('pmi_val400.npz')
+    texts, vocab = list(z['texts']), list(z['vocab'])
+    w, emap, count = pmi.cal_PMI_from_texts(texts, vocab, int(z['window']), int(z['min_cooc']), device=dev)
+    assert count == int(z['count'])
+    rows = np.repeat(np.arange(len(vocab)), np.diff(emap.rowptr))
+    assert np.array_equal(rows, z['rows']) and np.array_equal(emap.col, z['cols'])
+    assert np.array_equal(np.arange(1, count), z['ids'])
+    np.testing.assert_allclose(w.numpy(), z['weights'], rtol=1e-6)
+    # integer counts against the numpy oracle, cell by cell
+    pair, wc = PO.counts_numpy(*PO.encode(texts, vocab), len(vocab), int(z['window']))
+    rowptr, col, cnt = emap.pair_counts
+    dense = np.zeros_like(pair)
+    dense[np.repeat(np.arange(len(vocab)), np.diff(rowptr)), col] = cnt
+    pair[pair < int(z['min_cooc'])] = 0
+    assert np.array_equal(dense, pair) and np.array_equal(emap.word_count, wc)
+
+
+def test_pmi_counts_large_synthetic_checksums(dev):
+    """Full-size property check: the sum of all pair counts equals the number of (centre, target)
+    pairs the corpus contains, and sharding the corpus by document adds up exactly."""
+    from mgnns_b200 import ops
+    V, D, L, w = 20154, 20000, 100, 6
+    ids, lens, _ = synth.make_texts(D, V, L, seed=3)
+    tok = ids.to(torch.int32)
+    tok[ids == 1] = -1                     # treat UNK as out-of-vocabulary for this test
+    full = ops.pmi_count(tok.to(dev), V, w, 0, 1)
+    a = ops.pmi_count(tok[:D // 2].to(dev), V, w, 0, 1)
+    b = ops.pmi_count(tok[D // 2:].to(dev), V, w, 0, 1)
+    assert torch.equal(full[3], a[3] + b[3])
+    assert int(full[2].sum()) == int(a[2].sum()) + int(b[2].sum())
+    t = tok.numpy()
+    centre = (t > 0)
+    expected = 0
+    for off in range(-w, w):
+        if off == 0:
+            continue
+        c = centre[:, max(0, -off):L - max(0, off)]
+        tg = t[:, max(0, off):L + min(0, off)]
+        expected += int((c & (tg >= 0)).sum())
+    assert int(full[2].sum()) == expected
+    assert int(full[3].sum()) == int(centre.sum())
+
+
+# ------------------------------------------------------------------------------------------- whole model
+def build_model(dev, cfg, edge_map, edge_count, dropout=0.5):
+    from mgnns_b200.api.multi_gcn import IdentityTrunk, Multi_GCN_Multihead_Att
+    from mgnns_b200.api.text_gcn import Model as TextModel
+    opt = dict(emb_path='', bidirectional=True, hidden_size=cfg['hidden_size'], emb_size=300,
+               num_layers=cfg['num_layers'], dropout=dropout, emb_type='random', vocab_size=cfg['V'],
+               stack_num=cfg['stack_num'], n_head=cfg['n_head'], d_kv=cfg['d_kv'], is_regu=False)
+    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, cfg['V'])]
+    text_model = TextModel(cfg['num_labels'], 300, vocab, cfg['ngram'], 0.5, edge_count, edge_map,
+                           pmi=torch.zeros(edge_count, 1))
+    model = Multi_GCN_Multihead_Att(opt, cfg['num_labels'], text_model, IdentityTrunk(), IdentityTrunk(), 80, 365,
+                                    object_t=cfg['object_t'], place_t=cfg['place_t'], in_channel=300,
+                                    object_adj_file=synth.adj_dict('object'), place_adj_file=synth.adj_dict('place'))
+    synth.fill_parameters(model, seed=cfg['seed'])
+    return model.to(dev)
+
+
+def test_full_model_logits_and_grads_vs_reference_golden(dev, golden):
+    z, zp = golden('model.npz'), golden('pmi_synth300.npz')
+    cfg = H.MODEL_CFG
+    model = build_model(dev, cfg, H.edge_map_from_golden(zp, cfg['V']), int(zp['count'])).eval()
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    # eval-mode gradients: cuDNN's RNN backward refuses eval mode, so the (out-of-scope) LSTM runs on
+    # torch's native kernels for this check
+    with torch.backends.cudnn.flags(enabled=False):
+        logits = model(text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    close(model.text_features(text.to(dev)), z['text_feature'], 1e-4, 1e-5)
+    # north-star tolerance, fp32 mode
+    close(logits, z['logits'], 1e-3, 1e-4)
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), z['logits'].argmax(1))
+    loss = torch.nn.functional.cross_entropy(logits, labels.to(dev))
+    np.testing.assert_allclose(loss.item(), float(z['loss']), rtol=1e-4)
+    loss.backward()
+    norms = dict(zip(z['grad_names'], z['grad_norms']))
+    params = dict(model.named_parameters())
+    checked = 0
+    for n, ref in norms.items():
+        p = params[n]
+        if n.endswith('w_ks.bias'):
+            continue
+        assert p.grad is not None, n
+        np.testing.assert_allclose(p.grad.norm().item(), ref, rtol=5e-3, atol=1e-7, err_msg=n)
+        checked += 1
+    assert checked > 90
+    for k in z.files:
+        if k.startswith('grad::') and k[6:] in params:
+            close(params[k[6:]].grad, z[k], 5e-3, 5e-6, msg=k)
+    close(params['text_features.node_hidden.weight'].grad.sum(1), z['grad::node_hidden_rowsum'], 5e-3, 5e-6)
+    # parameters the reference never gives a gradient stay gradient-free (DDP bucket contract)
+    for n in ('rnn.weight_ih_l0', 'object_gate.weight', 'text_object_text_multi_head_att.slf_attn.fc.weight',
+              'object_linear_1.weight', 'text_features.Linear.weight'):
+        assert params[n].grad is None, n
+
+
+def test_full_model_bigger_batch_vs_oracle_and_mvsa_labels(dev):
+    """B=24 against the CPU oracle on a fresh seed, 7 and 3 labels (MVSA-shaped)."""
+    for num_labels, seed in ((7, 23), (3, 24)):
+        cfg = dict(H.MODEL_CFG, B=24, V=400, seed=seed, num_labels=num_labels)
+        emap, count = synth.synthetic_edge_map(cfg['V'], seed=seed, docs=800)
+        model = build_model(dev, cfg, emap, count).eval()
+        text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+        with torch.no_grad():
+            logits = model(text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+        P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        query = torch.from_numpy(synth.label_graphs()['label_glove'])[:num_labels]
+        with torch.no_grad():
+            ref = O.model_forward(P, text, lens, mask, fo, fp, oinp[0], pinp[0], query, lambda u, v: emap[u, v], cfg)
+        close(logits, ref, 1e-3, 1e-4)
+        assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
+
+
+def test_train_mode_step_is_finite_and_deterministic(dev):
+    cfg = dict(H.MODEL_CFG, B=8, V=300, seed=31)
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=31, docs=500)
+    model = build_model(dev, cfg, emap, count).train()
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    args = (text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(123)
+        model.zero_grad(set_to_none=True)
+        logits = model(*args)
+        loss = torch.nn.functional.cross_entropy(logits, labels.to(dev))
+        loss.backward()
+        outs.append((logits.detach().clone(), model.gc1.weight.grad.detach().clone()))
+        assert torch.isfinite(logits).all()
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                assert torch.isfinite(p.grad).all(), n
+    assert torch.equal(outs[0][0], outs[1][0])
+    close(outs[0][1], outs[1][1], 1e-4, 1e-6)   # float atomics may reorder sums
+
+
+def test_cpu_tensors_are_rejected(dev):
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.mgnns.mm(torch.randn(3, 3), torch.randn(3, 3), None, False, False, 0, 0.0)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.mgnns.add_layernorm(torch.randn(3, 8), None, torch.ones(8), torch.zeros(8), 1e-6)
