@@ -23,6 +23,45 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 _LIB = torch.library.Library("mgnns", "DEF")
 
 
+# ----------------------------------------------------------------------------- kernel timers
+class KernelTimers:
+    """Optional CUDA-event brackets around named kernel launches (bench.py's live roofline numbers).
+    Disabled by default: no events are recorded unless a name is enabled."""
+    enabled = set()
+    records = {}
+
+    @classmethod
+    def reset(cls, names=()):
+        cls.enabled = set(names)
+        cls.records = {n: [] for n in names}
+
+    @classmethod
+    def mean_ms(cls, name):
+        ev = cls.records.get(name, [])
+        return (sum(a.elapsed_time(b) for a, b in ev) / len(ev), len(ev)) if ev else (None, 0)
+
+
+class _timed:
+    __slots__ = ("name", "start")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self.name in KernelTimers.enabled:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        else:
+            self.start = None
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            KernelTimers.records[self.name].append((self.start, end))
+        return False
+
+
 # ----------------------------------------------------------------------------- helpers
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
@@ -260,10 +299,11 @@ def _spmm_raw(rowptr, col, val, x, n_rows):
         raise RuntimeError("mgnns::spmm_csr: rowptr has %d entries, expected %d" % (rowptr.numel(), n_rows + 1))
     for b0 in range(0, batch, 65535):
         nb = min(65535, batch - b0)
-        _check(_lib.mgnns_spmm_csr_f32(n_rows, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
-                                       x.data_ptr() + 4 * b0 * n_cols * F, F, n_cols * F,
-                                       y.data_ptr() + 4 * b0 * n_rows * F, F, n_rows * F,
-                                       F, nb, _stream()), "spmm_csr")
+        with _timed("spmm_csr"):
+            _check(_lib.mgnns_spmm_csr_f32(n_rows, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                           x.data_ptr() + 4 * b0 * n_cols * F, F, n_cols * F,
+                                           y.data_ptr() + 4 * b0 * n_rows * F, F, n_rows * F,
+                                           F, nb, _stream()), "spmm_csr")
     return y
 
 
@@ -408,9 +448,10 @@ def _attn_impl(u, bank, mask, scale, p_drop, seed):
     attn = torch.empty((H * B, 1, L), device=u.device, dtype=torch.float32)
     psum = torch.empty((B, H), device=u.device, dtype=torch.float32)
     lse = torch.empty((B, H), device=u.device, dtype=torch.float32)
-    _check(_lib.mgnns_attn_q1_fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale), float(p_drop),
-                                  seed & 0xFFFFFFFFFFFFFFFF, ctx.data_ptr(), attn.data_ptr(), psum.data_ptr(),
-                                  lse.data_ptr(), _stream()), "attn_q1_fwd")
+    with _timed("attn_q1_fwd"):
+        _check(_lib.mgnns_attn_q1_fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale),
+                                      float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, ctx.data_ptr(), attn.data_ptr(),
+                                      psum.data_ptr(), lse.data_ptr(), _stream()), "attn_q1_fwd")
     return ctx, attn, psum, lse
 
 
@@ -440,9 +481,11 @@ def _attn_backward(ctx, g_ctx, g_attn, g_psum, g_lse):
     g_psum = None if g_psum is None else _f32c(g_psum, "grad_psum")
     gu = torch.empty_like(u)
     gbank = torch.empty_like(bank)
-    _check(_lib.mgnns_attn_q1_bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
-                                  _ptr(g_psum), B, H, L, D, float(scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
-                                  gu.data_ptr(), gbank.data_ptr(), _stream()), "attn_q1_bwd")
+    with _timed("attn_q1_bwd"):
+        _check(_lib.mgnns_attn_q1_bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
+                                      _ptr(g_psum), B, H, L, D, float(scale), float(p_drop),
+                                      seed & 0xFFFFFFFFFFFFFFFF, gu.data_ptr(), gbank.data_ptr(), _stream()),
+               "attn_q1_bwd")
     return gu, gbank, None, None, None, None
 
 
@@ -581,12 +624,14 @@ def _imgbank_impl(fmap, weight, bias):
     pooled = torch.empty((B, C), device=fmap.device, dtype=torch.float32)
     argmax = torch.empty((B, C), device=fmap.device, dtype=torch.int32)
     s = _stream()
-    _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
+    with _timed("rowmax"):
+        _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
     # bank_b [P,O] = fmap_b^T [P,C] @ weight^T [C,O] + bias
     for b0 in range(0, B, 65535):
         nb = min(65535, B - b0)
-        gemm_raw(1, 1, P, O, C, (fmap, b0 * C * P), P, C * P, weight, C, 0, (bank, b0 * P * O), O, P * O,
-                 batch=nb, bias=bias)
+        with _timed("imgbank_fwd"):
+            gemm_raw(1, 1, P, O, C, (fmap, b0 * C * P), P, C * P, weight, C, 0, (bank, b0 * P * O), O, P * O,
+                     batch=nb, bias=bias)
     return bank, pooled, argmax
 
 
@@ -626,7 +671,8 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
         # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
         g_w = torch.zeros_like(weight)
         r = _pick_reduce(B)
-        gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, g_w, C, 0, batch=B, reduce=r, accumulate=1)
+        with _timed("imgbank_dw"):
+            gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, g_w, C, 0, batch=B, reduce=r, accumulate=1)
     if ctx.needs_input_grad[2] and g_bank is not None:
         g_b = colsum(g_bank.reshape(B * P, O))
     if ctx.needs_input_grad[0]:
