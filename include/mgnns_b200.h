@@ -168,6 +168,19 @@ int mgnns_rowmax_bwd_f32(const float* grad_pooled, const int32_t* argmax, int64_
                          float* grad_F, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Image-bank contraction on the tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *   fwd: bank[b,p,o] = sum_c fmap[b,c,p] * weight[o,c] + bias[o]
+ *   dw : gW[o,c]    += sum_{b,p} gbank[b,p,o] * fmap[b,c,p]      (gW initialised by the caller)
+ *   precision: 0 = TF32 operands, 1 = 3xTF32 split (fp32-class accuracy)
+ *   constraints: C % 32 == 0, P % 4 == 0, O % 4 == 0, O <= 304 (fwd) / 320 (dw)
+ * ref: self.liner_img_object / liner_img_place, models/Multi_GCN_Multihead_att.py:400-428
+ * ------------------------------------------------------------------------- */
+int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias,
+                         int B, int C, int P, int O, int precision, float* bank, void* stream);
+int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O,
+                        int precision, float* gW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * PMI co-occurrence counting (integer, bit-exact, order independent).
  *   tokens int32 [D, L]: vocab index, or -1 for out-of-vocabulary; pad_id is the
  *   vocab index of the literal 'PAD' token (centre positions equal to pad_id

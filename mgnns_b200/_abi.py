@@ -46,6 +46,8 @@ SIGNATURES = {
     "mgnns_pmi_count": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P]),
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),
     "mgnns_count_fill_csr_i32": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
+    "mgnns_imgbank_fwd_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "mgnns_imgbank_dw_tc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
 }
 # entry points added by optional translation units (tcgen05 paths); bound if present
 OPTIONAL_SIGNATURES = {}

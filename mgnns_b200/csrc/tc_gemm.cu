@@ -1,0 +1,533 @@
+// tcgen05 / TMEM / TMA contractions for the two streaming GEMMs of the image channel
+// (ref: nn.Linear(2048,300) over the 196 positions of the trunk output,
+//  models/Multi_GCN_Multihead_att.py:400-428, and its weight gradient).
+//
+//   FWD : bank_b[p, o]  = sum_c F_b[c, p] * W[o, c] + bias[o]          (M = p, N = o, K = c)
+//         A = F_b  read straight from the NCHW map (M-contiguous -> MN-major UMMA operand),
+//         B = W    (K-major).  One work item = (sample, 128-row tile of the 196 positions).
+//   DW  : gW[o, c]     += sum_{b,p} F_b[c, p] * gbank_b[p, o]           (M = c, N = o, K = (b,p))
+//         A = F_b (K-major), B = gbank_b (N-contiguous -> MN-major).  One work item =
+//         (128-channel tile, group of samples); fp32 atomicAdd of the partial tile.
+//
+// Pipeline (one CTA per SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// lane), warp 2 = TMEM allocator, warps 4-7 = operand splitter, warps 8-11 = epilogue
+// (tcgen05.ld -> bias -> global).  Operands are fp32 in shared memory (128-byte swizzle written by
+// TMA, out-of-bounds rows/columns zero-filled), consumed as kind::tf32.
+//
+// Precision modes: SPLIT=false is plain TF32 (10-bit mantissa operands).  SPLIT=true is the
+// "3xTF32" scheme: the splitter warps rewrite each landed tile in place as hi = x & ~0x1fff (exactly
+// representable in tf32) and write lo = x - hi to a second buffer; the issuer accumulates
+// hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator, which restores ~2^-21 relative accuracy
+// (fp32-class) at three times the tensor work.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace mgnns {
+namespace tc {
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (SM100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B (16-byte atoms; K-major operands),
+// 1 = SWIZZLE_128B_BASE32B (32-byte atoms) — the only layout the tensor core accepts for MN-major tf32
+// operands; it pairs with the TMA swizzle mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate.
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                     // c_format = F32
+         | (2u << 7) | (2u << 10)        // a_format = b_format = TF32
+         | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int KCHUNK = 32;               // fp32 elements per 128-byte swizzle row
+constexpr int UMMA_K = 8;                // tf32
+constexpr int NTHREADS = 384;
+constexpr int FWD = 0, DW = 1;
+
+struct Params {
+    int B, C, P, O;                      // samples, channels (2048), positions (196), outputs (300)
+    const float* bias;                   // FWD
+    float* out;                          // FWD: bank [B,P,O];  DW: gW [O,C]
+    int n_items;                         // FWD: B * m_tiles;   DW: c_tiles * groups
+    int m_tiles;                         // FWD: ceil(P/128)
+    int groups, samples_per_group;       // DW
+};
+
+template <int PROBLEM> struct Geo;
+template <> struct Geo<FWD> {
+    static constexpr int A_BYTES = 128 * KCHUNK * 4;          // 4 boxes of 32(p) x 32(c): MN-major
+    static constexpr int BN = 304;                            // 300 outputs padded to a multiple of 16
+    static constexpr int B_BYTES = BN * KCHUNK * 4;           // 2 boxes of 32(c) x 152(o): K-major
+    static constexpr int N0 = 160, N1 = 144;
+    static constexpr int A_MN = 1, B_MN = 0;
+};
+template <> struct Geo<DW> {
+    static constexpr int A_BYTES = 128 * KCHUNK * 4;          // 1 box of 32(p) x 128(c): K-major
+    static constexpr int BN = 320;
+    static constexpr int B_BYTES = BN * KCHUNK * 4;           // 10 boxes of 32(o) x 32(p): MN-major
+    static constexpr int N0 = 160, N1 = 160;
+    static constexpr int A_MN = 0, B_MN = 1;
+};
+
+template <int PROBLEM, bool SPLIT>
+struct Cfg {
+    using G = Geo<PROBLEM>;
+    static constexpr int STAGE_BYTES = (G::A_BYTES + G::B_BYTES) * (SPLIT ? 2 : 1);
+    static constexpr int STAGES = (226 * 1024 - 1024) / STAGE_BYTES >= 4 ? 4 : (226 * 1024 - 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int PROBLEM, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+    using G = Geo<PROBLEM>;
+    using CF = Cfg<PROBLEM, SPLIT>;
+    constexpr int STAGES = CF::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * CF::STAGE_BYTES);
+    uint64_t* full = bars;                       // TMA bytes landed
+    uint64_t* ready = bars + STAGES;             // (SPLIT) hi/lo tiles written
+    uint64_t* empty = bars + 2 * STAGES;         // MMAs that read the stage have completed
+    uint64_t* tmem_full = bars + 3 * STAGES;     // accumulator complete
+    uint64_t* tmem_empty = tmem_full + 1;        // accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    auto stageA = [&](int s) { return smem + s * CF::STAGE_BYTES; };
+    auto stageB = [&](int s) { return smem + s * CF::STAGE_BYTES + G::A_BYTES; };
+    auto stageAlo = [&](int s) { return smem + s * CF::STAGE_BYTES + G::A_BYTES + G::B_BYTES; };
+    auto stageBlo = [&](int s) { return smem + s * CF::STAGE_BYTES + 2 * G::A_BYTES + G::B_BYTES; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&ready[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // k-iterations of one work item
+    const int p_chunks = (p.P + KCHUNK - 1) / KCHUNK;
+    auto item_kiters = [&](int item) -> int {
+        if (PROBLEM == FWD) return p.C / KCHUNK;
+        const int g = item % p.groups;
+        const int b0 = g * p.samples_per_group;
+        const int nb = max(0, min(p.samples_per_group, p.B - b0));
+        return nb * p_chunks;
+    };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int kiters = item_kiters(item);
+                for (int kk = 0; kk < kiters; ++kk) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], G::A_BYTES + G::B_BYTES);
+                    uint8_t* a = stageA(stage);
+                    uint8_t* b = stageB(stage);
+                    if (PROBLEM == FWD) {
+                        const int smp = item / p.m_tiles, mt = item % p.m_tiles;
+                        const int c0 = kk * KCHUNK;
+                        // A: four 32(p) x 32(c) boxes -> MN-major atoms 4 KB apart
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_3d(a + j * 4096, &tmA, &full[stage], mt * 128 + j * 32, c0, smp);
+                        // B: two 152-row boxes of W[o, c0:c0+32]
+                        tma_load_2d(b, &tmB, &full[stage], c0, 0);
+                        tma_load_2d(b + 152 * 128, &tmB, &full[stage], c0, 152);
+                    } else {
+                        const int ct = item / p.groups, g = item % p.groups;
+                        const int smp = g * p.samples_per_group + kk / p_chunks;
+                        const int p0 = (kk % p_chunks) * KCHUNK;
+                        // A: F_b[c, p0:p0+32] for 128 channels (K-major)
+                        tma_load_3d(a, &tmA, &full[stage], p0, ct * 128, smp);
+                        // B: ten 32(o) x 32(p) boxes of gbank_b -> MN-major atoms 4 KB apart
+                        for (int j = 0; j < 10; ++j)
+                            tma_load_3d(b + j * 4096, &tmB, &full[stage], j * 32, p0, smp);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc0 = instr_desc_tf32(128, G::N0, G::A_MN, G::B_MN);
+            constexpr uint32_t idesc1 = instr_desc_tf32(128, G::N1, G::A_MN, G::B_MN);
+            // descriptor geometry
+            //   K-major  : 8-row groups 1024 B apart (SBO), k-step = +32 B inside the 128 B swizzle row
+            //   MN-major : 32-element atoms 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO), k-step (8 rows) = +1024 B,
+            //              layout SWIZZLE_128B_BASE32B
+            constexpr uint32_t A_LBO = G::A_MN ? 4096 : 16, A_SBO = G::A_MN ? 512 : 1024, A_KSTEP = G::A_MN ? 1024 : 32;
+            constexpr uint32_t B_LBO = G::B_MN ? 4096 : 16, B_SBO = G::B_MN ? 512 : 1024, B_KSTEP = G::B_MN ? 1024 : 32;
+            constexpr uint32_t A_LT = G::A_MN ? 1 : 2, B_LT = G::B_MN ? 1 : 2;
+            // second N part starts N0 rows (K-major: N0*128 B) or N0/32 atoms (MN-major: N0/32*4096 B) further
+            constexpr uint32_t B_PART1 = G::B_MN ? (G::N0 / 32) * 4096 : G::N0 * 128;
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int kiters = item_kiters(item);
+                mbar_wait(tmem_empty, tphase ^ 1);
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int kk = 0; kk < kiters; ++kk) {
+                    mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(stageA(stage)), b_hi = smem_u32(stageB(stage));
+                    const uint32_t a_lo = smem_u32(stageAlo(stage)), b_lo = smem_u32(stageBlo(stage));
+#pragma unroll
+                    for (int ks = 0; ks < KCHUNK / UMMA_K; ++ks) {
+                        const uint64_t dah = smem_desc(a_hi + ks * A_KSTEP, A_LBO, A_SBO, A_LT);
+                        const uint64_t dbh0 = smem_desc(b_hi + ks * B_KSTEP, B_LBO, B_SBO, B_LT);
+                        const uint64_t dbh1 = smem_desc(b_hi + B_PART1 + ks * B_KSTEP, B_LBO, B_SBO, B_LT);
+                        umma_tf32(tmem_base, dah, dbh0, idesc0, accumulate);
+                        umma_tf32(tmem_base + G::N0, dah, dbh1, idesc1, accumulate);
+                        accumulate = 1;
+                        if (SPLIT) {
+                            const uint64_t dal = smem_desc(a_lo + ks * A_KSTEP, A_LBO, A_SBO, A_LT);
+                            const uint64_t dbl0 = smem_desc(b_lo + ks * B_KSTEP, B_LBO, B_SBO, B_LT);
+                            const uint64_t dbl1 = smem_desc(b_lo + B_PART1 + ks * B_KSTEP, B_LBO, B_SBO, B_LT);
+                            umma_tf32(tmem_base, dal, dbh0, idesc0, 1);
+                            umma_tf32(tmem_base + G::N0, dal, dbh1, idesc1, 1);
+                            umma_tf32(tmem_base, dah, dbl0, idesc0, 1);
+                            umma_tf32(tmem_base + G::N0, dah, dbl1, idesc1, 1);
+                        }
+                    }
+                    umma_commit(&empty[stage]);          // frees the stage once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (kiters > 0) umma_commit(tmem_full);
+                else mbar_arrive(tmem_full);
+                tphase ^= 1;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================== operand splitter (3xTF32 only)
+        if (SPLIT) {
+            const int t = threadIdx.x - 128;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int kiters = item_kiters(item);
+                for (int kk = 0; kk < kiters; ++kk) {
+                    mbar_wait(&full[stage], phase);
+                    float4* hi = reinterpret_cast<float4*>(stageA(stage));
+                    float4* lo = reinterpret_cast<float4*>(stageAlo(stage));
+                    constexpr int NV = (G::A_BYTES + G::B_BYTES) / 16;     // A and B are contiguous, so are the lo buffers
+#pragma unroll 4
+                    for (int i = t; i < NV; i += 128) {
+                        float4 x = hi[i];
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================================================== epilogue (TMEM -> registers -> global)
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        uint32_t tphase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            mbar_wait(tmem_full, tphase);
+            tc_fence_after();
+            const int kiters = item_kiters(item);
+            if (kiters > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+                if (PROBLEM == FWD) {
+                    const int smp = item / p.m_tiles, mt = item % p.m_tiles;
+                    const int pp = mt * 128 + row;
+                    float* dst = p.out + ((int64_t)smp * p.P + pp) * p.O;
+                    for (int c0 = 0; c0 < G::BN; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + c0, r);
+                        tmem_ld_wait();
+                        if (pp < p.P) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const int o = c0 + j;
+                                if (o + 3 < p.O) {
+                                    float4 v;
+                                    v.x = __uint_as_float(r[j + 0]) + __ldg(p.bias + o + 0);
+                                    v.y = __uint_as_float(r[j + 1]) + __ldg(p.bias + o + 1);
+                                    v.z = __uint_as_float(r[j + 2]) + __ldg(p.bias + o + 2);
+                                    v.w = __uint_as_float(r[j + 3]) + __ldg(p.bias + o + 3);
+                                    *reinterpret_cast<float4*>(dst + o) = v;
+                                } else {
+                                    for (int e = 0; e < 4; ++e)
+                                        if (o + e < p.O) dst[o + e] = __uint_as_float(r[j + e]) + __ldg(p.bias + o + e);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    const int ct = item / p.groups;
+                    const int c = ct * 128 + row;
+                    for (int c0 = 0; c0 < G::BN; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + c0, r);
+                        tmem_ld_wait();
+                        if (c < p.C) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int o = c0 + j;
+                                if (o < p.O) atomicAdd(p.out + (int64_t)o * p.C + c, __uint_as_float(r[j]));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            tphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &st) == cudaSuccess &&
+            st == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// fp32 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first.
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool mn_major = false) {
+    EncodeTiledFn enc = get_encode();
+    MG_REQUIRE(enc != nullptr, "tc_gemm: cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MG_REQUIRE(rc == CUDA_SUCCESS, "tc_gemm: cuTensorMapEncodeTiled failed with code %d", (int)rc);
+    return 0;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int PROBLEM, bool SPLIT>
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, cudaStream_t st) {
+    using CF = Cfg<PROBLEM, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PROBLEM, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             CF::SMEM_BYTES);
+        MG_REQUIRE(e == cudaSuccess, "tc_gemm: cannot reserve %d bytes of shared memory: %s", CF::SMEM_BYTES,
+                   cudaGetErrorString(e));
+        configured = true;
+    }
+    int grid = sm_count();
+    if (grid > p.n_items) grid = p.n_items;
+    tc_gemm_kernel<PROBLEM, SPLIT><<<grid, NTHREADS, CF::SMEM_BYTES, st>>>(a, b, p);
+    MG_LAUNCH_CHECK("tc_gemm");
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace mgnns
+
+using namespace mgnns;
+using namespace mgnns::tc;
+
+// bank[B,P,O] = fmap[B,C,P]^T . weight[O,C]^T + bias ; precision: 0 = tf32, 1 = 3xTF32 (fp32-class)
+extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias, int B, int C, int P, int O,
+                                    int precision, float* bank, void* stream) {
+    MG_REQUIRE(B >= 0 && C >= 32 && P >= 1 && O >= 1, "imgbank_fwd_tc: bad dimensions");
+    MG_REQUIRE(C % KCHUNK == 0, "imgbank_fwd_tc: C=%d must be a multiple of 32", C);
+    MG_REQUIRE(O <= Geo<FWD>::BN && O % 4 == 0, "imgbank_fwd_tc: O=%d must be <= 304 and a multiple of 4", O);
+    MG_REQUIRE(P % 4 == 0, "imgbank_fwd_tc: P=%d must be a multiple of 4 (16-byte TMA strides)", P);
+    if (B == 0) return 0;
+    MG_REQUIRE(fmap && weight && bias && bank, "imgbank_fwd_tc: null pointer");
+    MG_REQUIRE(aligned16(fmap) && aligned16(weight) && aligned16(bank), "imgbank_fwd_tc: operands must be 16-byte aligned");
+    CUtensorMap ma, mb;
+    {
+        uint64_t dims[3] = {(uint64_t)P, (uint64_t)C, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)P * 4, (uint64_t)C * P * 4};
+        uint32_t box[3] = {32, 32, 1};
+        if (int rc = make_map(&ma, fmap, 3, dims, str, box, true)) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)C, (uint64_t)O};
+        uint64_t str[1] = {(uint64_t)C * 4};
+        uint32_t box[2] = {32, 152};
+        if (int rc = make_map(&mb, weight, 2, dims, str, box)) return rc;
+    }
+    Params p{};
+    p.B = B; p.C = C; p.P = P; p.O = O;
+    p.bias = bias; p.out = bank;
+    p.m_tiles = (P + 127) / 128;
+    p.n_items = B * p.m_tiles;
+    p.groups = 1; p.samples_per_group = 1;
+    cudaStream_t st = as_stream(stream);
+    return precision ? launch<FWD, true>(ma, mb, p, st) : launch<FWD, false>(ma, mb, p, st);
+}
+
+// gW[O,C] += sum_b gbank_b^T . fmap_b^T   (gW must be initialised by the caller)
+extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O, int precision,
+                                   float* gW, void* stream) {
+    MG_REQUIRE(B >= 0 && C >= 1 && P >= 1 && O >= 1, "imgbank_dw_tc: bad dimensions");
+    MG_REQUIRE(O <= Geo<DW>::BN && O % 4 == 0, "imgbank_dw_tc: O=%d must be <= 320 and a multiple of 4", O);
+    MG_REQUIRE(P % 4 == 0, "imgbank_dw_tc: P=%d must be a multiple of 4 (16-byte TMA strides)", P);
+    if (B == 0) return 0;
+    MG_REQUIRE(fmap && gbank && gW, "imgbank_dw_tc: null pointer");
+    MG_REQUIRE(aligned16(fmap) && aligned16(gbank), "imgbank_dw_tc: operands must be 16-byte aligned");
+    CUtensorMap ma, mb;
+    {
+        uint64_t dims[3] = {(uint64_t)P, (uint64_t)C, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)P * 4, (uint64_t)C * P * 4};
+        uint32_t box[3] = {32, 128, 1};
+        if (int rc = make_map(&ma, fmap, 3, dims, str, box)) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)O, (uint64_t)P, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)O * 4, (uint64_t)P * O * 4};
+        uint32_t box[3] = {32, 32, 1};
+        if (int rc = make_map(&mb, gbank, 3, dims, str, box, true)) return rc;
+    }
+    Params p{};
+    p.B = B; p.C = C; p.P = P; p.O = O;
+    p.bias = nullptr; p.out = gW;
+    const int c_tiles = (C + 127) / 128;
+    int groups = sm_count() / c_tiles;
+    if (groups < 1) groups = 1;
+    if (groups > B) groups = B;
+    p.groups = groups;
+    p.samples_per_group = (B + groups - 1) / groups;
+    p.m_tiles = 1;
+    p.n_items = c_tiles * groups;
+    cudaStream_t st = as_stream(stream);
+    return precision ? launch<DW, true>(ma, mb, p, st) : launch<DW, false>(ma, mb, p, st);
+}

@@ -9,6 +9,7 @@ Every op here:
     C-ABI calls.
 """
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -19,6 +20,32 @@ _lib = _abi.lib
 _check = _abi.check
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+# Precision mode of the two streaming image-bank contractions (everything else is fp32 FMA):
+#   "fp32"   exact fp32 CUDA-core GEMM (parity reference)
+#   "tf32x3" tcgen05 tensor cores with the 3xTF32 operand split (fp32-class accuracy)  [default]
+#   "tf32"   tcgen05 tensor cores, plain TF32 operands (looser bound)
+_PRECISIONS = {"fp32": None, "tf32x3": 1, "tf32": 0}
+_precision = os.environ.get("MGNNS_PRECISION", "tf32x3")
+if _precision not in _PRECISIONS:
+    raise RuntimeError("MGNNS_PRECISION must be one of %s" % sorted(_PRECISIONS))
+
+
+def set_precision(mode: str) -> str:
+    """Select the contraction mode; returns the previous one."""
+    global _precision
+    if mode not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+    prev, _precision = _precision, mode
+    return prev
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def _tc_ok(C, P, O, o_max):
+    return _PRECISIONS[_precision] is not None and C % 32 == 0 and P % 4 == 0 and O % 4 == 0 and O <= o_max
 
 _LIB = torch.library.Library("mgnns", "DEF")
 
@@ -627,6 +654,11 @@ def _imgbank_impl(fmap, weight, bias):
     with _timed("rowmax"):
         _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
     # bank_b [P,O] = fmap_b^T [P,C] @ weight^T [C,O] + bias
+    if _tc_ok(C, P, O, 304):
+        with _timed("imgbank_fwd"):
+            _check(_lib.mgnns_imgbank_fwd_tc(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
+                                             _PRECISIONS[_precision], bank.data_ptr(), s), "imgbank_fwd_tc")
+        return bank, pooled, argmax
     for b0 in range(0, B, 65535):
         nb = min(65535, B - b0)
         with _timed("imgbank_fwd"):
@@ -671,7 +703,12 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
         # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
         g_w = torch.zeros_like(weight)
         r = _pick_reduce(B)
-        with _timed("imgbank_dw"):
+        if _tc_ok(C, P, O, 320):
+            with _timed("imgbank_dw"):
+                _check(_lib.mgnns_imgbank_dw_tc(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
+                                                _PRECISIONS[_precision], g_w.data_ptr(), _stream()), "imgbank_dw_tc")
+        else:
+          with _timed("imgbank_dw"):
             gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, g_w, C, 0, batch=B, reduce=r, accumulate=1)
     if ctx.needs_input_grad[2] and g_bank is not None:
         g_b = colsum(g_bank.reshape(B * P, O))
