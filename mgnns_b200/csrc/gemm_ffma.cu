@@ -18,6 +18,8 @@ struct GemmParams {
     int reduce, accumulate;
     const float* bias; int act; float slope;
     int vecA, vecB, vecC;
+    int ksplit;        // >1: grid.z splits K of a single (A,B) pair, partial tiles are atomically added into C
+    int klen;          // K elements per split
 };
 
 constexpr int BK = 16;
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z;
 
-    const int ktiles = (p.K + BK - 1) / BK;
+    const int kbase = p.ksplit > 1 ? z * p.klen : 0;
+    const int kend = p.ksplit > 1 ? min(p.K, kbase + p.klen) : p.K;
+    const int ktiles = (kend - kbase + BK - 1) / BK;
     const int total = ktiles * p.reduce;
 
     float acc[4 * RM][4 * RN];
@@ -106,11 +110,11 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     float4 ra[NLA], rb[NLB];
     auto fetch = [&](int t) {
         int r = t / ktiles, kt = t - r * ktiles;
-        int64_t pair = (int64_t)z * p.reduce + r;
+        int64_t pair = p.ksplit > 1 ? 0 : (int64_t)z * p.reduce + r;
         // A is indexed by (m, k): TA means stored [k][m]
-        load_tile<BM, TA, NLA>(ra, p.A + pair * p.strideA, p.lda, m0, kt * BK, p.M, p.K, p.vecA, tid);
+        load_tile<BM, TA, NLA>(ra, p.A + pair * p.strideA, p.lda, m0, kbase + kt * BK, p.M, kend, p.vecA, tid);
         // B is indexed by (k, n): stored [k][n] (n contiguous) unless TB
-        load_tile<BN, !TB, NLB>(rb, p.B + pair * p.strideB, p.ldb, n0, kt * BK, p.N, p.K, p.vecB, tid);
+        load_tile<BN, !TB, NLB>(rb, p.B + pair * p.strideB, p.ldb, n0, kbase + kt * BK, p.N, kend, p.vecB, tid);
     };
 
     fetch(0);
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
         __syncthreads();
     }
 
-    float* Cz = p.C + (int64_t)z * p.strideC;
+    float* Cz = p.C + (p.ksplit > 1 ? 0 : (int64_t)z * p.strideC);
+    const bool add_bias = p.bias != nullptr && (p.ksplit <= 1 || z == 0);
 #pragma unroll
     for (int gi = 0; gi < RM; ++gi)
 #pragma unroll
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float x = acc[gi * 4 + i][gj * 4 + j];
-                    if (p.bias != nullptr && col + j < p.N) x += __ldg(p.bias + col + j);
+                    if (add_bias && col + j < p.N) x += __ldg(p.bias + col + j);
                     v[j] = apply_act(x, p.act, p.slope);
                 }
                 float* dst = Cz + (int64_t)row * p.ldc + col;
@@ -251,11 +256,32 @@ extern "C" int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
     p.vecA = aligned16(A) && (lda % 4 == 0) && (strideA % 4 == 0);
     p.vecB = aligned16(B) && (ldb % 4 == 0) && (strideB % 4 == 0);
     p.vecC = aligned16(C) && (ldc % 4 == 0) && (strideC % 4 == 0);
-    const int nz = batch / reduce;
+    int nz = batch / reduce;
     cudaStream_t st = as_stream(stream);
+    p.ksplit = 1;
+    p.klen = K;
     // big tiles only when they still fill the machine
     int64_t big_ctas = (int64_t)((M + 127) / 128) * ((N + 127) / 128) * nz;
     if (big_ctas >= 148 * 2) return launch_gemm<2, 2>(p, transA, transB, nz, st);
+    // a single small product (M = batch rows or a weight gradient with K = batch): split K across
+    // grid.z so that more than a handful of SMs work on it; partial tiles are summed with atomics
+    int64_t ctas = (int64_t)((M + 63) / 64) * ((N + 63) / 64) * nz;
+    if (batch == 1 && !accumulate && act == MGNNS_ACT_NONE && ctas < 148 && K >= 128) {
+        int split = (int)((148 * 2 + ctas - 1) / ctas);
+        int max_split = K / 64;
+        if (split > max_split) split = max_split;
+        if (split > 16) split = 16;
+        if (split > 1) {
+            int klen = ((K + split - 1) / split + BK - 1) / BK * BK;
+            split = (K + klen - 1) / klen;
+            cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
+            MG_REQUIRE(e == cudaSuccess, "gemm: memset failed: %s", cudaGetErrorString(e));
+            p.ksplit = split;
+            p.klen = klen;
+            p.accumulate = 1;
+            nz = split;
+        }
+    }
     return launch_gemm<1, 1>(p, transA, transB, nz, st);
 }
 
