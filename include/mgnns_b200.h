@@ -181,6 +181,24 @@ int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int
                         int precision, float* gW, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Length-aware bidirectional LSTM recurrence over compacted tokens (PyTorch gate order i,f,g,o).
+ *   offsets int32 [B+1] (first compact row of each sequence), lens int32 [B],
+ *   tiles int32 [n_tiles*8] (sequence ids grouped by similar length, -1 = empty slot)
+ *   G [N, 2*4H]: input projections x W_ih^T + b_ih + b_hh of both directions (forward | reverse)
+ *   wt4_* [H,H,4]: gate-interleaved transpose of W_hh (mgnns_lstm_prep_whh);  H even, <= 160
+ *   fwd writes Y [N,2H] (forward | reverse hidden states), gates [N,2,4,H] (post-activation),
+ *   csave [N,2,H], hprev [N,2,H];  bwd writes dG [N, 2*4H] (pre-activation gradients)
+ * ref: nn.LSTM over pack_padded_sequence, models/Multi_GCN_Multihead_att.py:376-384
+ * ------------------------------------------------------------------------- */
+int mgnns_lstm_prep_whh(const float* whh /* [4H,H] */, float* wt4, int H, void* stream);
+int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, const int32_t* tiles, int n_tiles,
+                       int H, const float* G, const float* wt4_f, const float* wt4_r, float* Y,
+                       float* gates, float* csave, float* hprev, void* stream);
+int mgnns_lstm_rec_bwd(const int32_t* offsets, const int32_t* lens, const int32_t* tiles, int n_tiles,
+                       int H, const float* dY, const float* gates, const float* csave,
+                       const float* whh_f, const float* whh_r, float* dG, void* stream);
+
+/* ---------------------------------------------------------------------------
  * PMI co-occurrence counting (integer, bit-exact, order independent).
  *   tokens int32 [D, L]: vocab index, or -1 for out-of-vocabulary; pad_id is the
  *   vocab index of the literal 'PAD' token (centre positions equal to pad_id

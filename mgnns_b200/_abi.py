@@ -48,6 +48,9 @@ SIGNATURES = {
     "mgnns_count_fill_csr_i32": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
     "mgnns_imgbank_fwd_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "mgnns_imgbank_dw_tc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "mgnns_lstm_prep_whh": (c_int, [P, P, c_int, P]),
+    "mgnns_lstm_rec_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "mgnns_lstm_rec_bwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P, P, P]),
 }
 # entry points added by optional translation units (tcgen05 paths); bound if present
 OPTIONAL_SIGNATURES = {}

@@ -241,22 +241,45 @@ class Multi_GCN_Multihead_Att(nn.Module):
         self.embedding.weight.data[pad_idx] = 0
 
     def get_text_memory_bank(self, text, text_lens, return_last_state=True):
-        """Embedding -> packed 2-layer bi-LSTM -> padded bank [B,L,300] (ref: model:366-398); cuDNN."""
+        """Embedding -> 2-layer bi-LSTM over the valid tokens only -> zero-padded bank [B,L,300]
+        (ref: model:366-398: pack_padded_sequence + cuDNN LSTM + pad_packed_sequence).  The recurrence
+        runs in mgnns::lstm_rec over compacted tokens; nn.LSTM only holds the parameters."""
         batch_size, max_text_len = list(text.size())
-        text_embed = self.embedding(text)
-        lens = text_lens.detach().to('cpu', torch.int64) if torch.is_tensor(text_lens) else torch.as_tensor(text_lens)
-        packed = nn.utils.rnn.pack_padded_sequence(text_embed, lens, batch_first=True, enforce_sorted=False)
-        memory_bank, (enc_final_state, _) = self.lstm(packed)
-        memory_bank, _ = nn.utils.rnn.pad_packed_sequence(memory_bank, batch_first=True, total_length=max_text_len)
-        memory_bank = memory_bank.contiguous()
+        dev = self.embedding.weight.device
+        plan = self.make_text_plan(text_lens, max_text_len)
+        tokens = text.to(dev).reshape(-1).index_select(0, plan.flat_idx)
+        text_embed = self.embedding(tokens)                                        # [N, emb]
+        y = ops.packed_bilstm(self.lstm, text_embed, plan, self.training)          # [N, 2H]
+        memory_bank = y.new_zeros(batch_size * max_text_len, y.shape[1]).index_copy(0, plan.flat_idx, y)
+        memory_bank = memory_bank.view(batch_size, max_text_len, y.shape[1])
         assert memory_bank.size() == torch.Size([batch_size, max_text_len, self.bi_hidden_size])
+        if not return_last_state:
+            return memory_bank
+        H = self.hidden_size
         if self.bidirectional:
-            last = torch.cat((enc_final_state[-1, :, :], enc_final_state[-2, :, :]), 1)
+            # ref: cat(enc_final_state[-1] (reverse), enc_final_state[-2] (forward)), model:392
+            last = torch.cat((y.index_select(0, plan.first_idx)[:, H:], y.index_select(0, plan.last_idx)[:, :H]), 1)
         else:
-            last = enc_final_state[-1, :, :]
-        if return_last_state:
-            return memory_bank, last
-        return memory_bank
+            last = y.index_select(0, plan.last_idx)
+        return memory_bank, last
+
+    def make_text_plan(self, text_lens, max_text_len):
+        """Length-sorted tile schedule + compact-token indices for the LSTM (host work on the CPU
+        lengths, one small H2D).  Memoised on the lengths tensor, so a data pipeline can call this
+        while prefetching a batch (on its copy stream) and forward() will find it."""
+        lens = text_lens if torch.is_tensor(text_lens) else torch.as_tensor(text_lens)
+        dev = self.embedding.weight.device
+        key = (lens.data_ptr(), lens._version, tuple(lens.shape), int(max_text_len), dev)
+        cache = self.__dict__.setdefault('_text_plans', {})
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is lens:
+            return hit[1]
+        import weakref
+        plan = ops.LstmPlan(lens, max_text_len, dev)
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        cache[key] = (weakref.ref(lens), plan)
+        return plan
 
     def _img_bank(self, feats, linear):
         bank, pooled, _ = torch.ops.mgnns.imgbank(feats, linear.weight, linear.bias)

@@ -266,7 +266,8 @@ extern "C" int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
     // a single small product (M = batch rows or a weight gradient with K = batch): split K across
     // grid.z so that more than a handful of SMs work on it; partial tiles are summed with atomics
     int64_t ctas = (int64_t)((M + 63) / 64) * ((N + 63) / 64) * nz;
-    if (batch == 1 && !accumulate && act == MGNNS_ACT_NONE && ctas < 148 && K >= 128) {
+    // (only for the weight-gradient shape, transA: forward products stay bitwise run-to-run deterministic)
+    if (transA && batch == 1 && !accumulate && act == MGNNS_ACT_NONE && ctas < 148 && K >= 128) {
         int split = (int)((148 * 2 + ctas - 1) / ctas);
         int max_split = K / 64;
         if (split > max_split) split = max_split;

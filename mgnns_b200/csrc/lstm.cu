@@ -1,0 +1,236 @@
+// Length-aware bidirectional LSTM recurrence over COMPACTED tokens (the reference
+// runs a packed cuDNN bi-LSTM, models/Multi_GCN_Multihead_att.py:366-398).
+//
+// The input projection x_t W_ih^T + b for every valid token is one dense GEMM done by the caller
+// (mgnns_gemm_f32 over the compact [N, in] matrix, N = sum of lengths), so padding (84 % of a
+// TumEmo batch) is never touched.  This file holds the sequential part: for a tile of TS sequences
+// of similar length (the host sorts by length) and one direction, a CTA steps through time keeping
+// h in shared memory and c in registers; every step is a [TS x H] x [H x 4H] product against W_hh
+// streamed from L2 with 128-bit loads (gate-interleaved transposed copy).  PyTorch gate order i,f,g,o.
+//
+// Forward saves the post-activation gates, the cell state and h_{t-1} per token; backward walks the
+// same tiles in reverse time and emits the pre-activation gradients dG, from which the caller gets
+// dW_ih / dx / db (GEMMs over the compact matrices) and dW_hh = dG^T . Hprev.
+#include "common.cuh"
+
+namespace mgnns {
+
+constexpr int TS = 8;        // sequences per tile
+constexpr int HP = 160;      // hidden size padded to a multiple of 32 (H <= 160)
+constexpr int LSTM_THREADS = HP * (TS / 2);   // thread = (unit, pair of sequences)
+
+struct LstmPlan {
+    const int32_t* offsets;   // [B+1] first compact row of each sequence
+    const int32_t* lens;      // [B]
+    const int32_t* tiles;     // [T*TS] sequence ids per tile, -1 = empty slot, sorted by length (desc)
+    int H;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// WT4[k][u][g] = Whh[g*H + u][k]
+__global__ void lstm_prep_whh_kernel(const float* __restrict__ whh, float* __restrict__ wt4, int H) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * H * 4) return;
+    int g = idx & 3, u = (idx >> 2) % H, k = (idx >> 2) / H;
+    wt4[idx] = whh[(int64_t)(g * H + u) * H + k];
+}
+
+// grid (tiles, 2 directions)
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_fwd_kernel(
+    LstmPlan plan, const float* __restrict__ G /* [N, 2*4H] */, const float* __restrict__ wt4_f,
+    const float* __restrict__ wt4_r, float* __restrict__ Y /* [N, 2H] */, float* __restrict__ gates /* [N,2,4,H] */,
+    float* __restrict__ csave /* [N,2,H] */, float* __restrict__ hprev /* [N,2,H] */) {
+    __shared__ float hs[2][TS][HP];
+    __shared__ int s_off[TS], s_len[TS];
+    const int H = plan.H;
+    const int dir = blockIdx.y;
+    const float4* __restrict__ W = reinterpret_cast<const float4*>(dir ? wt4_r : wt4_f);
+    const int u = threadIdx.x % HP, sp = threadIdx.x / HP;
+    if (threadIdx.x < TS) {
+        int s = plan.tiles[blockIdx.x * TS + threadIdx.x];
+        s_off[threadIdx.x] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[threadIdx.x] = s >= 0 ? plan.lens[s] : 0;
+    }
+    for (int i = threadIdx.x; i < 2 * TS * HP; i += LSTM_THREADS) (&hs[0][0][0])[i] = 0.f;
+    __syncthreads();
+    int tile_len = 0;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
+    const int sA = 2 * sp, sB = 2 * sp + 1;
+    const int lenA = s_len[sA], lenB = s_len[sB], offA = s_off[sA], offB = s_off[sB];
+    float cA = 0.f, cB = 0.f;
+    const bool live = u < H;
+    int cur = 0;
+    for (int t = 0; t < tile_len; ++t) {
+        float a[2][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { a[0][g] = 0.f; a[1][g] = 0.f; }
+        if (live) {
+            const float* hA = hs[cur][sA];
+            const float* hB = hs[cur][sB];
+#pragma unroll 5
+            for (int k = 0; k < H; ++k) {
+                const float4 w = __ldg(W + (int64_t)k * H + u);
+                const float x = hA[k], y = hB[k];
+                a[0][0] = fmaf(w.x, x, a[0][0]); a[0][1] = fmaf(w.y, x, a[0][1]);
+                a[0][2] = fmaf(w.z, x, a[0][2]); a[0][3] = fmaf(w.w, x, a[0][3]);
+                a[1][0] = fmaf(w.x, y, a[1][0]); a[1][1] = fmaf(w.y, y, a[1][1]);
+                a[1][2] = fmaf(w.z, y, a[1][2]); a[1][3] = fmaf(w.w, y, a[1][3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int len = q ? lenB : lenA, off = q ? offB : offA, s = q ? sB : sA;
+            float hold = hs[cur][s][u];
+            float hnew = hold;
+            if (live && t < len) {
+                const int tt = dir ? (len - 1 - t) : t;
+                const int64_t row = off + tt;
+                const float* g_in = G + row * (8 * H) + dir * 4 * H;
+                const float ig = sigmoidf_(a[q][0] + g_in[u]);
+                const float fg = sigmoidf_(a[q][1] + g_in[H + u]);
+                const float gg = tanhf(a[q][2] + g_in[2 * H + u]);
+                const float og = sigmoidf_(a[q][3] + g_in[3 * H + u]);
+                float& c = q ? cB : cA;
+                c = fg * c + ig * gg;
+                hnew = og * tanhf(c);
+                Y[row * (2 * H) + dir * H + u] = hnew;
+                float* gs = gates + (row * 2 + dir) * (4 * H);
+                gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
+                csave[(row * 2 + dir) * H + u] = c;
+                hprev[(row * 2 + dir) * H + u] = hold;
+            }
+            hs[cur ^ 1][s][u] = hnew;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
+    LstmPlan plan, const float* __restrict__ dY /* [N, 2H] */, const float* __restrict__ gates,
+    const float* __restrict__ csave, const float* __restrict__ whh_f /* [4H, H] */,
+    const float* __restrict__ whh_r, float* __restrict__ dG /* [N, 2*4H] */) {
+    __shared__ __align__(16) float dzs[4 * HP][TS];      // [gate row j][sequence]
+    __shared__ float part[4][TS][HP];
+    __shared__ float dh_rec[TS][HP];
+    __shared__ int s_off[TS], s_len[TS];
+    const int H = plan.H;
+    const int dir = blockIdx.y;
+    const float* __restrict__ W = dir ? whh_r : whh_f;
+    const int u = threadIdx.x % HP, sp = threadIdx.x / HP;
+    if (threadIdx.x < TS) {
+        int s = plan.tiles[blockIdx.x * TS + threadIdx.x];
+        s_off[threadIdx.x] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[threadIdx.x] = s >= 0 ? plan.lens[s] : 0;
+    }
+    for (int i = threadIdx.x; i < TS * HP; i += LSTM_THREADS) (&dh_rec[0][0])[i] = 0.f;
+    __syncthreads();
+    int tile_len = 0;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
+    const int sA = 2 * sp, sB = 2 * sp + 1;
+    const int lenA = s_len[sA], lenB = s_len[sB], offA = s_off[sA], offB = s_off[sB];
+    float dcA = 0.f, dcB = 0.f;
+    const bool live = u < H;
+    for (int t = tile_len - 1; t >= 0; --t) {
+        // ---- phase 1: gate gradients of this step ------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int len = q ? lenB : lenA, off = q ? offB : offA, s = q ? sB : sA;
+            float dz[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live && t < len) {
+                const int tt = dir ? (len - 1 - t) : t;
+                const int64_t row = off + tt;
+                const float* gs = gates + (row * 2 + dir) * (4 * H);
+                const float ig = gs[u], fg = gs[H + u], gg = gs[2 * H + u], og = gs[3 * H + u];
+                const float c = csave[(row * 2 + dir) * H + u];
+                float cprev = 0.f;
+                if (t > 0) {
+                    const int64_t rp = dir ? row + 1 : row - 1;
+                    cprev = csave[(rp * 2 + dir) * H + u];
+                }
+                const float dh = dY[row * (2 * H) + dir * H + u] + dh_rec[s][u];
+                const float tc = tanhf(c);
+                float& dc = q ? dcB : dcA;
+                const float dct = dc + dh * og * (1.f - tc * tc);
+                dz[0] = dct * gg * ig * (1.f - ig);
+                dz[1] = dct * cprev * fg * (1.f - fg);
+                dz[2] = dct * ig * (1.f - gg * gg);
+                dz[3] = dh * tc * og * (1.f - og);
+                dc = dct * fg;
+                float* out = dG + row * (8 * H) + dir * 4 * H;
+                out[u] = dz[0]; out[H + u] = dz[1]; out[2 * H + u] = dz[2]; out[3 * H + u] = dz[3];
+            }
+            if (live) {
+                dzs[u][s] = dz[0]; dzs[H + u][s] = dz[1]; dzs[2 * H + u][s] = dz[2]; dzs[3 * H + u][s] = dz[3];
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: dh_{t-1} = W_hh^T dz ; thread (k = u, gate block sp) over all TS sequences ------
+        if (t > 0) {
+            float acc[TS];
+#pragma unroll
+            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+            if (live) {
+                const int j0 = sp * H;
+#pragma unroll 5
+                for (int j = 0; j < H; ++j) {
+                    const float w = __ldg(W + (int64_t)(j0 + j) * H + u);
+                    const float4 d0 = *reinterpret_cast<const float4*>(&dzs[j0 + j][0]);
+                    const float4 d1 = *reinterpret_cast<const float4*>(&dzs[j0 + j][4]);
+                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
+                    acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
+                    acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < TS; ++s) part[sp][s][u] = acc[s];
+            __syncthreads();
+            dh_rec[sA][u] = part[0][sA][u] + part[1][sA][u] + part[2][sA][u] + part[3][sA][u];
+            dh_rec[sB][u] = part[0][sB][u] + part[1][sB][u] + part[2][sB][u] + part[3][sB][u];
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace mgnns
+
+using namespace mgnns;
+
+// wt4 [H,H,4] <- whh [4H,H]
+extern "C" int mgnns_lstm_prep_whh(const float* whh, float* wt4, int H, void* stream) {
+    MG_REQUIRE(H >= 1 && H <= HP, "lstm_prep_whh: hidden size %d unsupported (max %d)", H, HP);
+    MG_REQUIRE(whh && wt4, "lstm_prep_whh: null pointer");
+    int n = H * H * 4;
+    lstm_prep_whh_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(whh, wt4, H);
+    MG_LAUNCH_CHECK("lstm_prep_whh");
+    return 0;
+}
+
+extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, const int32_t* tiles, int n_tiles,
+                                  int H, const float* G, const float* wt4_f, const float* wt4_r, float* Y,
+                                  float* gates, float* csave, float* hprev, void* stream) {
+    MG_REQUIRE(H >= 1 && H <= HP && H % 2 == 0, "lstm_rec_fwd: hidden size %d unsupported (even, <= %d)", H, HP);
+    if (n_tiles == 0) return 0;
+    MG_REQUIRE(offsets && lens && tiles && G && wt4_f && wt4_r && Y && gates && csave && hprev, "lstm_rec_fwd: null pointer");
+    MG_REQUIRE(aligned16(wt4_f) && aligned16(wt4_r), "lstm_rec_fwd: transposed weights must be 16-byte aligned");
+    LstmPlan plan{offsets, lens, tiles, H};
+    lstm_rec_fwd_kernel<<<dim3(n_tiles, 2), LSTM_THREADS, 0, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+    MG_LAUNCH_CHECK("lstm_rec_fwd");
+    return 0;
+}
+
+extern "C" int mgnns_lstm_rec_bwd(const int32_t* offsets, const int32_t* lens, const int32_t* tiles, int n_tiles,
+                                  int H, const float* dY, const float* gates, const float* csave,
+                                  const float* whh_f, const float* whh_r, float* dG, void* stream) {
+    MG_REQUIRE(H >= 1 && H <= HP && H % 2 == 0, "lstm_rec_bwd: hidden size %d unsupported (even, <= %d)", H, HP);
+    if (n_tiles == 0) return 0;
+    MG_REQUIRE(offsets && lens && tiles && dY && gates && csave && whh_f && whh_r && dG, "lstm_rec_bwd: null pointer");
+    LstmPlan plan{offsets, lens, tiles, H};
+    lstm_rec_bwd_kernel<<<dim3(n_tiles, 2), LSTM_THREADS, 0, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+    MG_LAUNCH_CHECK("lstm_rec_bwd");
+    return 0;
+}

@@ -761,3 +761,140 @@ def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count:
     _check(_lib.mgnns_count_fill_csr_i32(pair.data_ptr(), V, V, min_count, rowptr.data_ptr(), col.data_ptr(),
                                          cnt.data_ptr(), s), "count_fill_csr")
     return rowptr, col, cnt, wc
+
+
+# ----------------------------------------------------------------------------- packed bi-LSTM recurrence
+LSTM_TILE = 8
+
+
+class LstmPlan:
+    """Host-side schedule for one batch of variable-length sequences (built from the CPU lengths the
+    reference already keeps on the host, engine:804 / model:376 — no device sync)."""
+
+    def __init__(self, lens_cpu: torch.Tensor, L: int, device):
+        import numpy as np
+        lens = lens_cpu.detach().to('cpu', torch.int64).numpy()
+        lens = np.clip(lens, 0, L)
+        B = lens.shape[0]
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        self.B, self.L, self.N = B, L, int(offsets[-1])
+        order = np.argsort(-lens, kind='stable')
+        order = order[lens[order] > 0]
+        n_tiles = (order.shape[0] + LSTM_TILE - 1) // LSTM_TILE
+        tiles = np.full(n_tiles * LSTM_TILE, -1, dtype=np.int64)
+        tiles[:order.shape[0]] = order
+        self.n_tiles = n_tiles
+        rows = np.repeat(np.arange(B, dtype=np.int64), lens)
+        pos = np.arange(self.N, dtype=np.int64) - offsets[rows]
+        flat = rows * L + pos
+        last = offsets[1:] - 1                      # compact row of each sequence's last token
+        packed = np.concatenate([offsets, lens, tiles]).astype(np.int32)
+        host = torch.from_numpy(packed).pin_memory() if torch.cuda.is_available() else torch.from_numpy(packed)
+        self.plan = host.to(device, non_blocking=True)
+        idx = torch.from_numpy(np.concatenate([flat, np.maximum(last, 0), offsets[:-1].clip(max=max(self.N - 1, 0))]))
+        idx = (idx.pin_memory() if torch.cuda.is_available() else idx).to(device, non_blocking=True)
+        self.flat_idx = idx[:self.N]                # compact row -> b*L + t
+        self.last_idx = idx[self.N:self.N + B]
+        self.first_idx = idx[self.N + B:]
+        self.offsets = self.plan[:B + 1]
+        self.lens = self.plan[B + 1:2 * B + 1]
+        self.tiles = self.plan[2 * B + 1:]
+        self.has_empty = bool((lens == 0).any())
+
+
+_LIB.define("lstm_rec(Tensor g, Tensor whh_f, Tensor whh_r, Tensor offsets, Tensor lens, Tensor tiles, int n_tiles) "
+            "-> (Tensor, Tensor, Tensor, Tensor)")
+
+
+def _lstm_check(g, whh_f, whh_r):
+    _need_cuda(g, whh_f, whh_r)
+    g = _f32c(g, "g")
+    whh_f = _f32c(whh_f, "whh_f")
+    whh_r = _f32c(whh_r, "whh_r")
+    H = whh_f.shape[1]
+    if whh_f.shape != (4 * H, H) or whh_r.shape != (4 * H, H) or g.dim() != 2 or g.shape[1] != 8 * H:
+        raise RuntimeError("mgnns::lstm_rec: expected g [N,8H], whh_* [4H,H]")
+    return g, whh_f, whh_r, H
+
+
+def _lstm_impl(g, whh_f, whh_r, offsets, lens, tiles, n_tiles):
+    g, whh_f, whh_r, H = _lstm_check(g, whh_f, whh_r)
+    N = g.shape[0]
+    dev = g.device
+    s = _stream()
+    wt4 = torch.empty((2, H, H, 4), device=dev, dtype=torch.float32)
+    _check(_lib.mgnns_lstm_prep_whh(whh_f.data_ptr(), wt4[0].data_ptr(), H, s), "lstm_prep_whh")
+    _check(_lib.mgnns_lstm_prep_whh(whh_r.data_ptr(), wt4[1].data_ptr(), H, s), "lstm_prep_whh")
+    y = torch.empty((N, 2 * H), device=dev, dtype=torch.float32)
+    gates = torch.empty((N, 2, 4, H), device=dev, dtype=torch.float32)
+    csave = torch.empty((N, 2, H), device=dev, dtype=torch.float32)
+    hprev = torch.empty((N, 2, H), device=dev, dtype=torch.float32)
+    with _timed("lstm_rec_fwd"):
+        _check(_lib.mgnns_lstm_rec_fwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), n_tiles, H, g.data_ptr(),
+                                       wt4[0].data_ptr(), wt4[1].data_ptr(), y.data_ptr(), gates.data_ptr(),
+                                       csave.data_ptr(), hprev.data_ptr(), s), "lstm_rec_fwd")
+    return y, gates, csave, hprev
+
+
+def _lstm_fake(g, whh_f, whh_r, offsets, lens, tiles, n_tiles):
+    H = whh_f.shape[1]
+    N = g.shape[0]
+    return g.new_empty((N, 2 * H)), g.new_empty((N, 2, 4, H)), g.new_empty((N, 2, H)), g.new_empty((N, 2, H))
+
+
+_LIB.impl("lstm_rec", _lstm_impl, "CUDA")
+torch.library.register_fake("mgnns::lstm_rec", _lstm_fake)
+
+
+def _lstm_setup(ctx, inputs, output):
+    g, whh_f, whh_r, offsets, lens, tiles, n_tiles = inputs
+    ctx.save_for_backward(whh_f, whh_r, offsets, lens, tiles, output[1], output[2], output[3])
+    ctx.n_tiles = n_tiles
+
+
+def _lstm_backward(ctx, gy, ggates, gc, ghp):
+    whh_f, whh_r, offsets, lens, tiles, gates, csave, hprev = ctx.saved_tensors
+    whh_f = _f32c(whh_f, "whh_f")
+    whh_r = _f32c(whh_r, "whh_r")
+    H = whh_f.shape[1]
+    gy = _f32c(gy, "grad_y")
+    N = gy.shape[0]
+    dG = torch.empty((N, 8 * H), device=gy.device, dtype=torch.float32)
+    with _timed("lstm_rec_bwd"):
+        _check(_lib.mgnns_lstm_rec_bwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), ctx.n_tiles, H,
+                                       gy.data_ptr(), gates.data_ptr(), csave.data_ptr(), whh_f.data_ptr(),
+                                       whh_r.data_ptr(), dG.data_ptr(), _stream()), "lstm_rec_bwd")
+    g_f = g_r = None
+    mm = torch.ops.mgnns.mm
+    if ctx.needs_input_grad[1]:
+        g_f = mm(dG[:, :4 * H], hprev[:, 0, :], None, True, False, ACT_NONE, 0.0)      # dWhh = dG^T . Hprev
+    if ctx.needs_input_grad[2]:
+        g_r = mm(dG[:, 4 * H:], hprev[:, 1, :], None, True, False, ACT_NONE, 0.0)
+    return (dG if ctx.needs_input_grad[0] else None), g_f, g_r, None, None, None, None
+
+
+torch.library.register_autograd("mgnns::lstm_rec", _lstm_backward, setup_context=_lstm_setup)
+
+
+def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, training: bool):
+    """Multi-layer bidirectional LSTM over compacted tokens with nn.LSTM's parameters (same names, same
+    math as torch's packed-sequence path, inter-layer dropout included).  Returns [N, 2H]."""
+    if not lstm.bidirectional or not lstm.batch_first or lstm.proj_size != 0:
+        raise NotImplementedError("mgnns_b200 packed_bilstm: bidirectional, batch_first, no projection only")
+    x = x_compact
+    for layer in range(lstm.num_layers):
+        sfx = "_l%d" % layer
+        w_ih = torch.cat([getattr(lstm, "weight_ih" + sfx), getattr(lstm, "weight_ih" + sfx + "_reverse")], 0)
+        if lstm.bias:
+            b = torch.cat([getattr(lstm, "bias_ih" + sfx) + getattr(lstm, "bias_hh" + sfx),
+                           getattr(lstm, "bias_ih" + sfx + "_reverse") + getattr(lstm, "bias_hh" + sfx + "_reverse")], 0)
+        else:
+            b = None
+        g = torch.ops.mgnns.mm(x, w_ih, b, False, True, ACT_NONE, 0.0)                      # [N, 8H]
+        y = torch.ops.mgnns.lstm_rec(g, getattr(lstm, "weight_hh" + sfx), getattr(lstm, "weight_hh" + sfx + "_reverse"),
+                                     plan.offsets, plan.lens, plan.tiles, plan.n_tiles)[0]
+        if layer + 1 < lstm.num_layers and training and lstm.dropout > 0:
+            y = torch.nn.functional.dropout(y, lstm.dropout, True)
+        x = y
+    return x

@@ -374,6 +374,43 @@ def test_label_attention_matches_reference_golden_and_grads(dev, golden):
     assert torch.equal(o1, o2)
 
 
+# ------------------------------------------------------------------------------------------- packed bi-LSTM
+@pytest.mark.parametrize("B,L,seed", [(5, 12, 0), (37, 100, 1), (8, 100, 2)])
+def test_packed_bilstm_vs_torch_lstm(dev, ops, B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    if seed == 2:
+        lens[:] = torch.tensor([100, 100, 1, 1, 2, 50, 99, 3])
+    x = torch.randn(B, L, 300, generator=g)
+    ref = torch.nn.LSTM(300, 150, num_layers=2, bidirectional=True, batch_first=True, dropout=0.5).eval()
+    synth.fill_parameters(ref, seed=seed)
+    xr = x.clone().double().requires_grad_()
+    refd = ref.double()
+    packed = torch.nn.utils.rnn.pack_padded_sequence(xr, lens, batch_first=True, enforce_sorted=False)
+    out, (hn, _) = refd(packed)
+    bank_ref, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True, total_length=L)
+    r = torch.randn(B, L, 300, generator=g)
+    (bank_ref * r.double()).sum().backward()
+
+    mine = torch.nn.LSTM(300, 150, num_layers=2, bidirectional=True, batch_first=True, dropout=0.5).eval()
+    synth.fill_parameters(mine, seed=seed)
+    mine = mine.to(dev)
+    plan = ops.LstmPlan(lens, L, dev)
+    assert plan.N == int(lens.sum())
+    xg = x.to(dev).requires_grad_()
+    xc = xg.reshape(B * L, 300).index_select(0, plan.flat_idx)
+    y = ops.packed_bilstm(mine, xc, plan, False)
+    bank = y.new_zeros(B * L, 300).index_copy(0, plan.flat_idx, y).view(B, L, 300)
+    close(bank, bank_ref, 1e-4, 1e-5)
+    # final states: forward direction at the last token, reverse direction at the first token
+    close(y.index_select(0, plan.last_idx)[:, :150], hn[-2], 1e-4, 1e-5)
+    close(y.index_select(0, plan.first_idx)[:, 150:], hn[-1], 1e-4, 1e-5)
+    (bank * r.to(dev)).sum().backward()
+    close(xg.grad, xr.grad, 1e-3, 1e-5)
+    for (n, p), (_, q) in zip(mine.named_parameters(), refd.named_parameters()):
+        close(p.grad, q.grad, 1e-3, 2e-5, msg=n)
+
+
 # ------------------------------------------------------------------------------------------- image bank
 @pytest.mark.parametrize("mode,rtol,atol", [("fp32", 1e-4, 1e-4), ("tf32x3", 1e-4, 1e-4), ("tf32", 5e-3, 5e-2)])
 @pytest.mark.parametrize("B", [5, 37])
