@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--cpu-batch', type=int, default=32, help='samples per CPU-baseline step (cfg 1)')
     ap.add_argument('--no-cfg2', action='store_true', help='skip the cfg-2 GraphConvolution microbench')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='do not capture the step in a CUDA graph')
     return ap.parse_args()
 
 
@@ -185,8 +186,9 @@ def host_batch(B, seed):
 
 def to_device(hb, dev, B):
     d = {k: (v.to(dev, non_blocking=True) if k != 'lens' else v) for k, v in hb.items()}
-    d['oinp'] = d['oinp'].expand(B, -1, -1)
-    d['pinp'] = d['pinp'].expand(B, -1, -1)
+    d['oinp_base'], d['pinp_base'] = d['oinp'], d['pinp']
+    d['oinp'] = d['oinp_base'].expand(B, -1, -1)
+    d['pinp'] = d['pinp_base'].expand(B, -1, -1)
     return d
 
 
@@ -279,8 +281,9 @@ def ours(args):
 
     emap, count = synth.synthetic_edge_map(VOCAB, seed=0, docs=20000)
     model = build_model(dev, emap, count).train()
-    opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5)
-    reducer = GradientAllReducer(model) if world > 1 else None
+    use_graph = not args.eager
+    opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5, capturable=use_graph)
+    reducer = GradientAllReducer(model) if (world > 1 and not use_graph) else None
     crit = torch.nn.CrossEntropyLoss()
 
     # two distinct batches per rank (3.3 GB of inputs per pair >> 126 MB L2), alternating
@@ -295,6 +298,8 @@ def ours(args):
         loss.backward()
         if reducer is not None:
             reducer.finish()
+        elif world > 1:
+            raise RuntimeError("eager multi-GPU step needs the reducer")
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
         opt.step()
         return loss
@@ -305,28 +310,45 @@ def ours(args):
         torch.cuda.synchronize()
 
     torch.manual_seed(1234 + rank)
+    launch_mode, graph_note, gsteps, launches_per_step = "eager", None, None, None
+    if use_graph:
+        try:
+            from mgnns_b200.graph_step import GraphedTrainStep
+            gsteps = []
+            for d in dbs:
+                l0 = _abi.launch_count()
+                gsteps.append(GraphedTrainStep(model, opt, crit, d, clip_norm=10.0, world_size=world, warmup=2))
+                launches_per_step = (_abi.launch_count() - l0) // 3       # 2 warm-up steps + 1 captured step
+            launch_mode = "cuda_graph"
+        except Exception as exc:            # capture is an optimisation, never a correctness dependency
+            graph_note = "graph capture failed, eager step used: %s" % str(exc)[:300]
+            gsteps = None
+            opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5)
+            reducer = GradientAllReducer(model) if world > 1 else None
+
+    def run_step(i):
+        if gsteps is not None:
+            return gsteps[i % 2].replay()
+        return step(dbs[i % 2])
+
     for i in range(W):
-        step(dbs[i % 2])
+        run_step(i)
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    timer_names = ['imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd']
-    ops.KernelTimers.reset(timer_names)
     launches0 = _abi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(K):
-        step(dbs[i % 2])
+        run_step(i)
     e1.record()
     barrier()
-    launches = _abi.launch_count() - launches0
+    launches = (_abi.launch_count() - launches0) if gsteps is None else launches_per_step * K
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
-    kt = {n: ops.KernelTimers.mean_ms(n) for n in timer_names}
-    ops.KernelTimers.reset([])
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,31 +358,39 @@ def ours(args):
     # ---- end-to-end: pinned host inputs -> H2D (prefetched on a copy stream) -> step -> loss.item() -----
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def prefetch(hb):
+    def prefetch(i):
+        """H2D of batch i into its static device buffers (+ its LSTM schedule), on the copy stream."""
+        hb, d = hbs[i % 2], dbs[i % 2]
         with torch.cuda.stream(copy_stream):
-            d = to_device(hb, dev, B)
-            model.make_text_plan(hb['lens'], CFG['L'])     # LSTM schedule travels with the batch
+            if gsteps is not None:
+                gsteps[i % 2].update_lengths(hb['lens'])
+            else:
+                model.make_text_plan(d['lens'], CFG['L'])
+            for k, v in hb.items():
+                if k in ('oinp', 'pinp'):
+                    d[k + '_base'].copy_(v, non_blocking=True)      # [1,N,300]; the model sees it expanded to [B,N,300]
+                elif k != 'lens':
+                    d[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return d, ev
+        return ev
 
     for i in range(2):                      # warm the e2e path
-        d, ev = prefetch(hbs[i % 2])
+        ev = prefetch(i)
         torch.cuda.current_stream().wait_event(ev)
-        step(d).item()
+        run_step(i).item()
     barrier()
     E = max(4, K // 2)
     t0 = time.perf_counter()
-    nxt = prefetch(hbs[0])
+    ev = prefetch(0)
     for i in range(E):
-        d, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
+        loss = run_step(i)
+        done = torch.cuda.Event()
+        done.record()
         if i + 1 < E:
-            nxt = prefetch(hbs[(i + 1) % 2])
-        loss = step(d)
-        for v in d.values():
-            if torch.is_tensor(v) and v.is_cuda:
-                v.record_stream(torch.cuda.current_stream())
+            # the other buffer was last read by step i-1, which has completed (loss.item() below syncs every step)
+            ev = prefetch(i + 1)
         loss_val = loss.item()              # device -> host read of the step's result
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -369,6 +399,24 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * E / t.item()
 
+    # ---- per-kernel timing pass (eager, same inputs): CUDA events around the hand-written kernels -------
+    timer_names = ['imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd', 'lstm_rec_fwd', 'lstm_rec_bwd']
+    opt_e = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5)
+    red_e = GradientAllReducer(model) if world > 1 else None
+    saved = (opt, reducer)
+    opt, reducer = opt_e, red_e
+    KT = 4
+    step(dbs[0])
+    torch.cuda.synchronize()
+    ops.KernelTimers.reset(timer_names)
+    for i in range(KT):
+        step(dbs[i % 2])
+    torch.cuda.synchronize()
+    kt = {n: ops.KernelTimers.mean_ms(n) for n in timer_names}
+    ops.KernelTimers.reset([])
+    opt, reducer = saved
+    payload = red_e.payload_bytes() if red_e is not None else 0
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,7 +424,7 @@ def ours(args):
 
     # ---- roofline of the dominant hand-written kernel -------------------------------------------------
     C, P_, O_ = 2048, 196, 300
-    cand = {n: (ms or 0.0) * cnt for n, (ms, cnt) in kt.items()}
+    cand = {n: (ms or 0.0) * cnt for n, (ms, cnt) in kt.items() if n in ('imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd')}
     dom = max(cand, key=cand.get)
     dom_ms, dom_cnt = kt[dom]
     flop = {'imgbank_fwd': 2.0 * B * P_ * C * O_, 'imgbank_dw': 2.0 * B * P_ * C * O_}
@@ -390,17 +438,17 @@ def ours(args):
         ach = flop[dom] / (dom_ms * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
-                "share_of_step": dom_ms * dom_cnt / K / ms_step,
+                "share_of_step": dom_ms * dom_cnt / KT / ms_step,
                 "peak_source": peaks['source'] + "; TF32 = bf16_tflops_sustained/2",
                 "algorithmic_flop_per_launch": flop[dom], "algorithmic_bytes_per_launch": byts[dom]}
     else:
         ach = byts[dom] / (dom_ms * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks['hbm_gbs'], "unit": "GB/s",
                 "frac": ach / peaks['hbm_gbs'], "traffic": None, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
-                "share_of_step": dom_ms * dom_cnt / K / ms_step, "peak_source": peaks['source'],
+                "share_of_step": dom_ms * dom_cnt / KT / ms_step, "peak_source": peaks['source'],
                 "algorithmic_bytes_per_launch": byts[dom]}
-    kernels = {n: {"ms_per_launch": ms, "launches_per_step": cnt / K,
-                   "gbs": (byts[n] / (ms * 1e-3) / 1e9) if ms else None,
+    kernels = {n: {"ms_per_launch": ms, "launches_per_step": cnt / KT,
+                   "gbs": (byts[n] / (ms * 1e-3) / 1e9) if (ms and n in byts) else None,
                    "tflops": (flop[n] / (ms * 1e-3) / 1e12) if (ms and n in flop) else None}
                for n, (ms, cnt) in kt.items()}
 
@@ -410,7 +458,9 @@ def ours(args):
             "config": {"workload": WORKLOAD % B, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (1.65 GB of feature maps per step; two alternating batches)",
-                       "precision_mode": "fp32 (CUDA-core FMA contractions)"},
+                       "precision_mode": "%s for the image-bank contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
+                       "launch": launch_mode, "launch_note": graph_note,
+                       "kernel_timing": "per-kernel numbers from a separate eager pass of %d steps on the same inputs (CUDA events)" % KT},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(hbs[0]),
                     "d2h_bytes_per_step": 4, "steps": E, "last_loss": loss_val,
@@ -419,7 +469,7 @@ def ours(args):
             "gpu_launches": int(launches),
             "roofline": roof, "kernels": kernels}
     if world > 1:
-        line["allreduce_payload_bytes"] = reducer.payload_bytes()
+        line["allreduce_payload_bytes"] = payload
         dist.destroy_process_group()
     if world == 1:
         del dbs

@@ -116,16 +116,18 @@ int mgnns_text_maxagg_bwd(const int64_t* doc_ids, int B, int L, int max_length, 
  *   ctx[b,h,:] = sum_l pt[b,h,l] * bank[b,l,:];  psum[b,h] = sum_l pt[b,h,l]
  *   attn[h*B+b, l] = pt   (the reference's head-major [H*B,1,L] layout)
  *   lse[b,h] = logsumexp_l(s)  (saved for backward)
+ *   seed_offset: optional device pointer whose value is added to `seed` inside the kernel, so a
+ *   captured CUDA graph draws fresh dropout masks on every replay (NULL = use `seed` as is)
  * D % 4 == 0, D <= 512.
  * ref: models/submodules.py:68-78 (projections folded by the caller), :106-119
  * ------------------------------------------------------------------------- */
 int mgnns_attn_q1_fwd(const float* u, const float* bank, const float* mask,
                       int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
-                      float* ctx, float* attn, float* psum, float* lse, void* stream);
+                      const uint64_t* seed_offset, float* ctx, float* attn, float* psum, float* lse, void* stream);
 int mgnns_attn_q1_bwd(const float* u, const float* bank, const float* mask, const float* lse,
                       const float* grad_ctx, const float* grad_psum /* may be NULL */,
                       int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
-                      float* grad_u, float* grad_bank, void* stream);
+                      const uint64_t* seed_offset, float* grad_u, float* grad_bank, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Label-query element-wise attention:
@@ -135,12 +137,12 @@ int mgnns_attn_q1_bwd(const float* u, const float* bank, const float* mask, cons
  * ------------------------------------------------------------------------- */
 int mgnns_label_attn_fwd(const float* Q, const float* K, const float* V, int64_t ldkv,
                          int B, int C, int heads, int dh, float inv_scale,
-                         float p_drop, uint64_t seed, float* out, void* stream);
+                         float p_drop, uint64_t seed, const uint64_t* seed_offset, float* out, void* stream);
 /* grad_Q [C,heads*dh] is accumulated (atomicAdd, pre-zeroed by caller);
  * grad_K / grad_V [B, heads*dh] with row stride ldg are overwritten          */
 int mgnns_label_attn_bwd(const float* Q, const float* K, const float* V, int64_t ldkv,
                          int B, int C, int heads, int dh, float inv_scale,
-                         float p_drop, uint64_t seed, const float* grad_out,
+                         float p_drop, uint64_t seed, const uint64_t* seed_offset, const float* grad_out,
                          float* grad_Q, float* grad_K, float* grad_V, int64_t ldg, void* stream);
 
 /* ---------------------------------------------------------------------------

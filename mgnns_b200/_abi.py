@@ -31,13 +31,13 @@ SIGNATURES = {
                                       P, P, P, c_int, P, P]),
     "mgnns_text_maxagg_bwd": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int64,
                                       P, P, P, c_int, P, P, P, P, P]),
-    "mgnns_attn_q1_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+    "mgnns_attn_q1_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                   P, P, P, P, P]),
-    "mgnns_attn_q1_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+    "mgnns_attn_q1_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                   P, P, P]),
-    "mgnns_label_attn_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+    "mgnns_label_attn_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                      P, P]),
-    "mgnns_label_attn_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64,
+    "mgnns_label_attn_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                      P, P, P, P, c_int64, P]),
     "mgnns_add_layernorm_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, P]),
     "mgnns_add_layernorm_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_float, P, P, P, P]),

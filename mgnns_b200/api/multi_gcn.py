@@ -247,11 +247,12 @@ class Multi_GCN_Multihead_Att(nn.Module):
         batch_size, max_text_len = list(text.size())
         dev = self.embedding.weight.device
         plan = self.make_text_plan(text_lens, max_text_len)
-        tokens = text.to(dev).reshape(-1).index_select(0, plan.flat_idx)
+        tokens = text.to(dev).reshape(-1).index_select(0, plan.tok_idx)
         text_embed = self.embedding(tokens)                                        # [N, emb]
         y = ops.packed_bilstm(self.lstm, text_embed, plan, self.training)          # [N, 2H]
-        memory_bank = y.new_zeros(batch_size * max_text_len, y.shape[1]).index_copy(0, plan.flat_idx, y)
-        memory_bank = memory_bank.view(batch_size, max_text_len, y.shape[1])
+        # scatter back to the padded layout; plan padding rows land in one dummy row that is sliced off
+        memory_bank = y.new_zeros(batch_size * max_text_len + 1, y.shape[1]).index_copy(0, plan.flat_idx, y)
+        memory_bank = memory_bank[:batch_size * max_text_len].view(batch_size, max_text_len, y.shape[1])
         assert memory_bank.size() == torch.Size([batch_size, max_text_len, self.bi_hidden_size])
         if not return_last_state:
             return memory_bank
@@ -263,7 +264,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
             last = y.index_select(0, plan.last_idx)
         return memory_bank, last
 
-    def make_text_plan(self, text_lens, max_text_len):
+    def make_text_plan(self, text_lens, max_text_len, capacity=None):
         """Length-sorted tile schedule + compact-token indices for the LSTM (host work on the CPU
         lengths, one small H2D).  Memoised on the lengths tensor, so a data pipeline can call this
         while prefetching a batch (on its copy stream) and forward() will find it."""
@@ -275,7 +276,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
         if hit is not None and hit[0]() is lens:
             return hit[1]
         import weakref
-        plan = ops.LstmPlan(lens, max_text_len, dev)
+        plan = ops.LstmPlan(lens, max_text_len, dev, capacity)
         if len(cache) >= 4:
             cache.pop(next(iter(cache)))
         cache[key] = (weakref.ref(lens), plan)
@@ -320,10 +321,17 @@ class Multi_GCN_Multihead_Att(nn.Module):
         return ops.linear(att, x_linear.weight, x_linear.bias)                  # [B, 300]
 
     def _query(self):
+        """Label GloVe query matrix on the model's device (cached: the reference re-uploads it every
+        forward, model:462-468)."""
         q = self.label_query if self.label_query is not None else _default_label_embedding()
         if q.shape[0] < self.num_labels:
             raise ValueError("label query matrix has %d rows, model has %d labels" % (q.shape[0], self.num_labels))
-        return q[:self.num_labels]
+        dev = self.gc1.weight.device
+        hit = self.__dict__.get('_query_dev')
+        if hit is None or hit[0] is not q or hit[1].device != dev:
+            hit = (q, q[:self.num_labels].to(device=dev, dtype=torch.float32))
+            self.__dict__['_query_dev'] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ forward (ref: model:431-567)
     def forward(self, text, text_lens, text_mask, object_feature, place_feature, object_inp, place_inp,

@@ -30,7 +30,7 @@ __device__ __forceinline__ void scale4(float4& acc, float s) { acc.x *= s; acc.y
 template <int NV>
 __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask,
-    int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+    int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
     float* __restrict__ ctx, float* __restrict__ attn, float* __restrict__ psum, float* __restrict__ lse) {
     extern __shared__ __align__(16) float sm[];
     float* us = sm;                          // [HG][D]
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D4 = D >> 2;
     const float inv_keep = 1.f / (1.f - p_drop);
+    if (seed_offset != nullptr) seed += *seed_offset;      // device-resident epoch (CUDA-graph replays)
 
     for (int i = threadIdx.x; i < HG * D; i += AT_THREADS)
         us[i] = (i < nh * D) ? u[((int64_t)b * H + h0) * D + i] : 0.f;
@@ -179,7 +180,7 @@ template <int NV>
 __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask,
     const float* __restrict__ lse, const float* __restrict__ gctx, const float* __restrict__ gpsum,
-    int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+    int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
     float* __restrict__ gu, float* __restrict__ gbank) {
     extern __shared__ __align__(16) float sm[];
     float* us = sm;                      // [HG][D]
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
     const float* bk = bank + (int64_t)b * L * D;
     const float* mk = mask ? mask + (int64_t)b * L : nullptr;
     float* gb = gbank + (int64_t)b * L * D;
+    if (seed_offset != nullptr) seed += *seed_offset;
 
     for (int h0 = 0; h0 < H; h0 += HG) {
         const int nh = min(HG, H - h0);
@@ -341,7 +343,7 @@ using namespace mgnns;
     } while (0)
 
 extern "C" int mgnns_attn_q1_fwd(const float* u, const float* bank, const float* mask,
-                                 int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                                 int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
                                  float* ctx, float* attn, float* psum, float* lse, void* stream) {
     MG_REQUIRE(B >= 0 && H >= 1 && L >= 1 && D >= 4, "attn_q1_fwd: bad dimensions");
     MG_REQUIRE(D % 4 == 0 && D <= 512, "attn_q1_fwd: D=%d must be a multiple of 4 and <= 512", D);
@@ -357,10 +359,10 @@ extern "C" int mgnns_attn_q1_fwd(const float* u, const float* bank, const float*
     dim3 grid(B, (H + HG - 1) / HG);
     const int nv = (D / 4 + 31) / 32;
     switch (nv) {
-        case 1: AT_DISPATCH(1, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, ctx, attn, psum, lse); break;
-        case 2: AT_DISPATCH(2, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, ctx, attn, psum, lse); break;
-        case 3: AT_DISPATCH(3, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, ctx, attn, psum, lse); break;
-        default: AT_DISPATCH(4, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, ctx, attn, psum, lse); break;
+        case 1: AT_DISPATCH(1, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
+        case 2: AT_DISPATCH(2, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
+        case 3: AT_DISPATCH(3, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
+        default: AT_DISPATCH(4, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
     }
     MG_LAUNCH_CHECK("attn_q1_fwd");
     return 0;
@@ -368,7 +370,7 @@ extern "C" int mgnns_attn_q1_fwd(const float* u, const float* bank, const float*
 
 extern "C" int mgnns_attn_q1_bwd(const float* u, const float* bank, const float* mask, const float* lse,
                                  const float* grad_ctx, const float* grad_psum,
-                                 int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                                 int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
                                  float* grad_u, float* grad_bank, void* stream) {
     MG_REQUIRE(B >= 0 && H >= 1 && L >= 1 && D >= 4, "attn_q1_bwd: bad dimensions");
     MG_REQUIRE(D % 4 == 0 && D <= 512, "attn_q1_bwd: D=%d must be a multiple of 4 and <= 512", D);
@@ -383,10 +385,10 @@ extern "C" int mgnns_attn_q1_bwd(const float* u, const float* bank, const float*
     dim3 grid(B);
     const int nv = (D / 4 + 31) / 32;
     switch (nv) {
-        case 1: AT_DISPATCH(1, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, grad_u, grad_bank); break;
-        case 2: AT_DISPATCH(2, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, grad_u, grad_bank); break;
-        case 3: AT_DISPATCH(3, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, grad_u, grad_bank); break;
-        default: AT_DISPATCH(4, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, grad_u, grad_bank); break;
+        case 1: AT_DISPATCH(1, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, seed_offset, grad_u, grad_bank); break;
+        case 2: AT_DISPATCH(2, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, seed_offset, grad_u, grad_bank); break;
+        case 3: AT_DISPATCH(3, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, seed_offset, grad_u, grad_bank); break;
+        default: AT_DISPATCH(4, attn_q1_bwd_kernel, smem, grid, u, bank, mask, lse, grad_ctx, grad_psum, B, H, L, D, scale, p_drop, seed, seed_offset, grad_u, grad_bank); break;
     }
     MG_LAUNCH_CHECK("attn_q1_bwd");
     return 0;

@@ -6,7 +6,7 @@
 // TumEmo batch) is never touched.  This file holds the sequential part: for a tile of TS sequences
 // of similar length (the host sorts by length) and one direction, a CTA steps through time keeping
 // h in shared memory and c in registers; every step is a [TS x H] x [H x 4H] product against W_hh
-// streamed from L2 with 128-bit loads (gate-interleaved transposed copy).  PyTorch gate order i,f,g,o.
+// streamed from L2 (transposed copy, every element fetched once per CTA and step).  PyTorch gate order i,f,g,o.
 //
 // Forward saves the post-activation gates, the cell state and h_{t-1} per token; backward walks the
 // same tiles in reverse time and emits the pre-activation gradients dG, from which the caller gets
@@ -27,32 +27,40 @@ struct LstmPlan {
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// tanh through one accurate expf: 1 - 2/(1+e^{2x}); |error| ~1e-7, saturates correctly at +-inf
+__device__ __forceinline__ float tanhf_(float x) { return 1.f - 2.f / (1.f + expf(2.f * x)); }
 
-// WT4[k][u][g] = Whh[g*H + u][k]
-__global__ void lstm_prep_whh_kernel(const float* __restrict__ whh, float* __restrict__ wt4, int H) {
+constexpr int KCH = 16;      // W_hh elements fetched per thread before they are consumed (memory-level parallelism)
+
+// WT[k][j] = Whh[j][k]   (j = gate*H + unit)
+__global__ void lstm_prep_whh_kernel(const float* __restrict__ whh, float* __restrict__ wt, int H) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * H * 4) return;
-    int g = idx & 3, u = (idx >> 2) % H, k = (idx >> 2) / H;
-    wt4[idx] = whh[(int64_t)(g * H + u) * H + k];
+    int j = idx % (4 * H), k = idx / (4 * H);
+    wt[idx] = whh[(int64_t)j * H + k];
 }
 
-// grid (tiles, 2 directions)
+// grid (tiles, 2 directions).  Per step: (1) thread j < 4H computes the recurrent pre-activation
+// z[s][j] = sum_k WT[k][j] h[s][k] for all TS sequences (every W element is loaded exactly once per
+// CTA and step, KCH loads in flight per thread); (2) thread (unit, sequence pair) applies the gates.
 __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_fwd_kernel(
-    LstmPlan plan, const float* __restrict__ G /* [N, 2*4H] */, const float* __restrict__ wt4_f,
-    const float* __restrict__ wt4_r, float* __restrict__ Y /* [N, 2H] */, float* __restrict__ gates /* [N,2,4,H] */,
+    LstmPlan plan, const float* __restrict__ G /* [N, 2*4H] */, const float* __restrict__ wt_f,
+    const float* __restrict__ wt_r, float* __restrict__ Y /* [N, 2H] */, float* __restrict__ gates /* [N,2,4,H] */,
     float* __restrict__ csave /* [N,2,H] */, float* __restrict__ hprev /* [N,2,H] */) {
-    __shared__ float hs[2][TS][HP];
+    __shared__ __align__(16) float hs[2][HP][TS];        // [buffer][k][sequence]
+    __shared__ float zs[TS][4 * HP];
     __shared__ int s_off[TS], s_len[TS];
     const int H = plan.H;
     const int dir = blockIdx.y;
-    const float4* __restrict__ W = reinterpret_cast<const float4*>(dir ? wt4_r : wt4_f);
+    const float* __restrict__ W = dir ? wt_r : wt_f;
+    const int j = threadIdx.x;
     const int u = threadIdx.x % HP, sp = threadIdx.x / HP;
     if (threadIdx.x < TS) {
         int s = plan.tiles[blockIdx.x * TS + threadIdx.x];
         s_off[threadIdx.x] = s >= 0 ? plan.offsets[s] : 0;
         s_len[threadIdx.x] = s >= 0 ? plan.lens[s] : 0;
     }
-    for (int i = threadIdx.x; i < 2 * TS * HP; i += LSTM_THREADS) (&hs[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * HP * TS; i += LSTM_THREADS) (&hs[0][0][0])[i] = 0.f;
     __syncthreads();
     int tile_len = 0;
 #pragma unroll
@@ -61,47 +69,58 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_fwd_kernel(
     const int lenA = s_len[sA], lenB = s_len[sB], offA = s_off[sA], offB = s_off[sB];
     float cA = 0.f, cB = 0.f;
     const bool live = u < H;
+    const bool jlive = j < 4 * H;
     int cur = 0;
     for (int t = 0; t < tile_len; ++t) {
-        float a[2][4];
+        if (jlive) {
+            float acc[TS];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { a[0][g] = 0.f; a[1][g] = 0.f; }
-        if (live) {
-            const float* hA = hs[cur][sA];
-            const float* hB = hs[cur][sB];
-#pragma unroll 5
-            for (int k = 0; k < H; ++k) {
-                const float4 w = __ldg(W + (int64_t)k * H + u);
-                const float x = hA[k], y = hB[k];
-                a[0][0] = fmaf(w.x, x, a[0][0]); a[0][1] = fmaf(w.y, x, a[0][1]);
-                a[0][2] = fmaf(w.z, x, a[0][2]); a[0][3] = fmaf(w.w, x, a[0][3]);
-                a[1][0] = fmaf(w.x, y, a[1][0]); a[1][1] = fmaf(w.y, y, a[1][1]);
-                a[1][2] = fmaf(w.z, y, a[1][2]); a[1][3] = fmaf(w.w, y, a[1][3]);
+            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+            for (int k0 = 0; k0 < H; k0 += KCH) {
+                float w[KCH];
+#pragma unroll
+                for (int i = 0; i < KCH; ++i) w[i] = (k0 + i < H) ? __ldg(W + (int64_t)(k0 + i) * (4 * H) + j) : 0.f;
+#pragma unroll
+                for (int i = 0; i < KCH; ++i) {
+                    if (k0 + i < H) {
+                        const float4 h0 = *reinterpret_cast<const float4*>(&hs[cur][k0 + i][0]);
+                        const float4 h1 = *reinterpret_cast<const float4*>(&hs[cur][k0 + i][4]);
+                        acc[0] = fmaf(w[i], h0.x, acc[0]); acc[1] = fmaf(w[i], h0.y, acc[1]);
+                        acc[2] = fmaf(w[i], h0.z, acc[2]); acc[3] = fmaf(w[i], h0.w, acc[3]);
+                        acc[4] = fmaf(w[i], h1.x, acc[4]); acc[5] = fmaf(w[i], h1.y, acc[5]);
+                        acc[6] = fmaf(w[i], h1.z, acc[6]); acc[7] = fmaf(w[i], h1.w, acc[7]);
+                    }
+                }
             }
+#pragma unroll
+            for (int s = 0; s < TS; ++s) zs[s][j] = acc[s];
         }
+        __syncthreads();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int len = q ? lenB : lenA, off = q ? offB : offA, s = q ? sB : sA;
-            float hold = hs[cur][s][u];
-            float hnew = hold;
-            if (live && t < len) {
-                const int tt = dir ? (len - 1 - t) : t;
-                const int64_t row = off + tt;
-                const float* g_in = G + row * (8 * H) + dir * 4 * H;
-                const float ig = sigmoidf_(a[q][0] + g_in[u]);
-                const float fg = sigmoidf_(a[q][1] + g_in[H + u]);
-                const float gg = tanhf(a[q][2] + g_in[2 * H + u]);
-                const float og = sigmoidf_(a[q][3] + g_in[3 * H + u]);
-                float& c = q ? cB : cA;
-                c = fg * c + ig * gg;
-                hnew = og * tanhf(c);
-                Y[row * (2 * H) + dir * H + u] = hnew;
-                float* gs = gates + (row * 2 + dir) * (4 * H);
-                gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
-                csave[(row * 2 + dir) * H + u] = c;
-                hprev[(row * 2 + dir) * H + u] = hold;
+            if (live) {
+                const float hold = hs[cur][u][s];
+                float hnew = hold;
+                if (t < len) {
+                    const int tt = dir ? (len - 1 - t) : t;
+                    const int64_t row = off + tt;
+                    const float* g_in = G + row * (8 * H) + dir * 4 * H;
+                    const float ig = sigmoidf_(zs[s][u] + g_in[u]);
+                    const float fg = sigmoidf_(zs[s][H + u] + g_in[H + u]);
+                    const float gg = tanhf_(zs[s][2 * H + u] + g_in[2 * H + u]);
+                    const float og = sigmoidf_(zs[s][3 * H + u] + g_in[3 * H + u]);
+                    float& c = q ? cB : cA;
+                    c = fg * c + ig * gg;
+                    hnew = og * tanhf_(c);
+                    Y[row * (2 * H) + dir * H + u] = hnew;
+                    float* gs = gates + (row * 2 + dir) * (4 * H);
+                    gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
+                    csave[(row * 2 + dir) * H + u] = c;
+                    hprev[(row * 2 + dir) * H + u] = hold;
+                }
+                hs[cur ^ 1][u][s] = hnew;
             }
-            hs[cur ^ 1][s][u] = hnew;
         }
         __syncthreads();
         cur ^= 1;
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
                     cprev = csave[(rp * 2 + dir) * H + u];
                 }
                 const float dh = dY[row * (2 * H) + dir * H + u] + dh_rec[s][u];
-                const float tc = tanhf(c);
+                const float tc = tanhf_(c);
                 float& dc = q ? dcB : dcA;
                 const float dct = dc + dh * og * (1.f - tc * tc);
                 dz[0] = dct * gg * ig * (1.f - ig);
@@ -175,15 +194,21 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
             for (int s = 0; s < TS; ++s) acc[s] = 0.f;
             if (live) {
                 const int j0 = sp * H;
-#pragma unroll 5
-                for (int j = 0; j < H; ++j) {
-                    const float w = __ldg(W + (int64_t)(j0 + j) * H + u);
-                    const float4 d0 = *reinterpret_cast<const float4*>(&dzs[j0 + j][0]);
-                    const float4 d1 = *reinterpret_cast<const float4*>(&dzs[j0 + j][4]);
-                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
-                    acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
-                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
-                    acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                for (int jb = 0; jb < H; jb += KCH) {
+                    float w[KCH];
+#pragma unroll
+                    for (int i = 0; i < KCH; ++i) w[i] = (jb + i < H) ? __ldg(W + (int64_t)(j0 + jb + i) * H + u) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < KCH; ++i) {
+                        if (jb + i < H) {
+                            const float4 d0 = *reinterpret_cast<const float4*>(&dzs[j0 + jb + i][0]);
+                            const float4 d1 = *reinterpret_cast<const float4*>(&dzs[j0 + jb + i][4]);
+                            acc[0] = fmaf(w[i], d0.x, acc[0]); acc[1] = fmaf(w[i], d0.y, acc[1]);
+                            acc[2] = fmaf(w[i], d0.z, acc[2]); acc[3] = fmaf(w[i], d0.w, acc[3]);
+                            acc[4] = fmaf(w[i], d1.x, acc[4]); acc[5] = fmaf(w[i], d1.y, acc[5]);
+                            acc[6] = fmaf(w[i], d1.z, acc[6]); acc[7] = fmaf(w[i], d1.w, acc[7]);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
 
 using namespace mgnns;
 
-// wt4 [H,H,4] <- whh [4H,H]
+// wt [H,4H] <- whh [4H,H] (transpose)
 extern "C" int mgnns_lstm_prep_whh(const float* whh, float* wt4, int H, void* stream) {
     MG_REQUIRE(H >= 1 && H <= HP, "lstm_prep_whh: hidden size %d unsupported (max %d)", H, HP);
     MG_REQUIRE(whh && wt4, "lstm_prep_whh: null pointer");
@@ -216,7 +241,6 @@ extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, c
     MG_REQUIRE(H >= 1 && H <= HP && H % 2 == 0, "lstm_rec_fwd: hidden size %d unsupported (even, <= %d)", H, HP);
     if (n_tiles == 0) return 0;
     MG_REQUIRE(offsets && lens && tiles && G && wt4_f && wt4_r && Y && gates && csave && hprev, "lstm_rec_fwd: null pointer");
-    MG_REQUIRE(aligned16(wt4_f) && aligned16(wt4_r), "lstm_rec_fwd: transposed weights must be 16-byte aligned");
     LstmPlan plan{offsets, lens, tiles, H};
     lstm_rec_fwd_kernel<<<dim3(n_tiles, 2), LSTM_THREADS, 0, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
     MG_LAUNCH_CHECK("lstm_rec_fwd");

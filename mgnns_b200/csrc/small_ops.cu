@@ -25,7 +25,9 @@ constexpr int LA_MAXE = 4;  // elements per lane -> dh <= 128
 
 __global__ void __launch_bounds__(256) label_attn_fwd_kernel(
     const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ldkv,
-    int B, int C, int heads, int dh, float inv_scale, float p_drop, uint64_t seed, float* __restrict__ out) {
+    int B, int C, int heads, int dh, float inv_scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
+    float* __restrict__ out) {
+    if (seed_offset != nullptr) seed += *seed_offset;
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t total = (int64_t)B * C * heads;
@@ -72,10 +74,11 @@ __global__ void __launch_bounds__(256) label_attn_fwd_kernel(
 constexpr int LA_BS = 4;
 __global__ void __launch_bounds__(256) label_attn_bwd_kernel(
     const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int64_t ldkv,
-    int B, int C, int heads, int dh, float inv_scale, float p_drop, uint64_t seed,
+    int B, int C, int heads, int dh, float inv_scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
     const float* __restrict__ gout, float* __restrict__ gQ, float* __restrict__ gK, float* __restrict__ gV,
     int64_t ldg) {
     extern __shared__ float sm[];
+    if (seed_offset != nullptr) seed += *seed_offset;
     const int HD = heads * dh;
     float* sQ = sm;               // [C*HD]
     float* sK = sQ + C * HD;      // [HD]
@@ -336,7 +339,7 @@ extern "C" int64_t mgnns_launch_count(void) { return g_launches.load(std::memory
 
 extern "C" int mgnns_label_attn_fwd(const float* Q, const float* K, const float* V, int64_t ldkv,
                                     int B, int C, int heads, int dh, float inv_scale,
-                                    float p_drop, uint64_t seed, float* out, void* stream) {
+                                    float p_drop, uint64_t seed, const uint64_t* seed_offset, float* out, void* stream) {
     MG_REQUIRE(B >= 0 && C >= 1 && heads >= 1 && dh >= 1, "label_attn_fwd: bad dimensions");
     MG_REQUIRE(dh <= 32 * LA_MAXE, "label_attn_fwd: head dim %d > %d unsupported", dh, 32 * LA_MAXE);
     MG_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "label_attn_fwd: p_drop must be in [0,1)");
@@ -346,14 +349,14 @@ extern "C" int mgnns_label_attn_fwd(const float* Q, const float* K, const float*
     int64_t blocks = (warps + 7) / 8;
     MG_REQUIRE(blocks < (1LL << 31), "label_attn_fwd: problem too large");
     label_attn_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(Q, K, V, ldkv, B, C, heads, dh, inv_scale,
-                                                                           p_drop, seed, out);
+                                                                           p_drop, seed, seed_offset, out);
     MG_LAUNCH_CHECK("label_attn_fwd");
     return 0;
 }
 
 extern "C" int mgnns_label_attn_bwd(const float* Q, const float* K, const float* V, int64_t ldkv,
                                     int B, int C, int heads, int dh, float inv_scale,
-                                    float p_drop, uint64_t seed, const float* grad_out,
+                                    float p_drop, uint64_t seed, const uint64_t* seed_offset, const float* grad_out,
                                     float* grad_Q, float* grad_K, float* grad_V, int64_t ldg, void* stream) {
     MG_REQUIRE(B >= 0 && C >= 1 && heads >= 1 && dh >= 1, "label_attn_bwd: bad dimensions");
     MG_REQUIRE(dh <= 32 * LA_MAXE, "label_attn_bwd: head dim %d > %d unsupported", dh, 32 * LA_MAXE);
@@ -366,7 +369,7 @@ extern "C" int mgnns_label_attn_bwd(const float* Q, const float* K, const float*
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(label_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     label_attn_bwd_kernel<<<(B + LA_BS - 1) / LA_BS, 256, smem, as_stream(stream)>>>(
-        Q, K, V, ldkv, B, C, heads, dh, inv_scale, p_drop, seed, grad_out, grad_Q, grad_K, grad_V, ldg);
+        Q, K, V, ldkv, B, C, heads, dh, inv_scale, p_drop, seed, seed_offset, grad_out, grad_Q, grad_K, grad_V, ldg);
     MG_LAUNCH_CHECK("label_attn_bwd");
     return 0;
 }

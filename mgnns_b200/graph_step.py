@@ -1,0 +1,87 @@
+"""Whole-step CUDA-graph capture of the MGNNS training step (forward + loss + backward +
+gradient all-reduce + clip_grad_norm_ + optimizer step).
+
+The eager step issues ~3,000 small launches and is bound by Python/launch overhead; replaying a
+captured graph removes that.  What makes the step capturable:
+  * inputs live in static device tensors (the caller copies / H2D-transfers a batch into them);
+  * the LSTM schedule is a fixed-capacity LstmPlan refreshed in place (ops.LstmPlan.update_);
+  * dropout seeds come from a device-resident counter advanced inside the graph (ops.set_seed_tensor);
+  * the optimizer is constructed with capturable=True.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, criterion, batch, clip_norm=10.0, world_size=1, plan_capacity=None,
+                 warmup=3):
+        """batch: dict of STATIC tensors — text i64 [B,L], mask f32 [B,L], fo/fp f32 [B,2048,14,14],
+        oinp/pinp, labels (all on the model's device) and lens (int64, CPU)."""
+        self.model, self.opt, self.crit, self.batch = model, optimizer, criterion, batch
+        self.clip_norm, self.world = clip_norm, world_size
+        dev = batch['text'].device
+        L = batch['text'].shape[1]
+        n = int(batch['lens'].clamp(max=L).sum())
+        cap = plan_capacity if plan_capacity is not None else ((n + 1023) // 1024) * 1024
+        self.lens_key = batch['lens']                      # identity of this tensor keys the plan cache
+        self.plan = model.make_text_plan(self.lens_key, L, capacity=cap)
+        self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.loss = None
+        self.graph = None
+        self._flat = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        prev = ops.set_seed_tensor(self.seed)
+        timers = ops.KernelTimers.enabled
+        ops.KernelTimers.enabled = set()
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+                self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+        finally:
+            ops.set_seed_tensor(prev)
+            ops.KernelTimers.enabled = timers
+
+    def _allreduce(self):
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        if self._flat is None:
+            total = sum(p.numel() for p in params)
+            self._flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
+        off = 0
+        for p in params:
+            self._flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._flat.div_(self.world)
+        off = 0
+        for p in params:
+            p.grad.copy_(self._flat[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
+
+    def _step(self):
+        b = self.batch
+        self.opt.zero_grad(set_to_none=True)
+        logits = self.model(b['text'], self.lens_key, b['mask'], b['fo'], b['fp'], b['oinp'], b['pinp'])
+        loss = self.crit(logits, b['labels'])
+        loss.backward()
+        if self.world > 1:
+            self._allreduce()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
+        self.opt.step()
+        return loss.detach()
+
+    def update_lengths(self, lens_cpu):
+        """New batch in the static buffers: refresh the LSTM schedule (tiny H2D on the current stream)."""
+        self.plan.update_(lens_cpu)
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

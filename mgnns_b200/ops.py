@@ -94,8 +94,12 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream on the current device (cheap C call)
+    return _raw_stream(torch.cuda.current_device())
 
 
 def _need_cuda(*tensors):
@@ -124,6 +128,20 @@ def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.size(1) == 1 and t.stride(0) < 1:
         t = t.contiguous()
     return t
+
+
+_seed_tensor = None     # optional CUDA int64[1] added to every dropout seed inside the kernels (graph replays)
+
+
+def set_seed_tensor(t):
+    """Install (or clear with None) a device-resident seed offset; GraphedTrainStep advances it once per replay."""
+    global _seed_tensor
+    prev, _seed_tensor = _seed_tensor, t
+    return prev
+
+
+def _seed_ptr():
+    return None if _seed_tensor is None else _seed_tensor.data_ptr()
 
 
 def new_seed() -> int:
@@ -156,18 +174,42 @@ def _mm_shapes(a, b, trans_a, trans_b):
     return M, N, K
 
 
+_gemm = _lib.mgnns_gemm_f32
+_f32 = torch.float32
+
+
 def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
-    _need_cuda(a, b, bias)
-    a = _rows2d(a, "a")
-    b = _rows2d(b, "b")
-    M, N, K = _mm_shapes(a, b, trans_a, trans_b)
+    # hot wrapper (about 150 calls per training step): checks are folded into as few Python operations as possible
+    if not (a.is_cuda and b.is_cuda and a.dtype is _f32 and b.dtype is _f32 and a.dim() == 2 and b.dim() == 2):
+        _need_cuda(a, b, bias)
+        a = _rows2d(a, "a")
+        b = _rows2d(b, "b")
+    if a.stride(1) != 1 or b.stride(1) != 1:
+        a = _rows2d(a, "a")
+        b = _rows2d(b, "b")
+    if trans_a:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if trans_b:
+        N, Kb = b.shape
+    else:
+        Kb, N = b.shape
+    if K != Kb:
+        raise RuntimeError("mgnns::mm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    bp = None
     if bias is not None:
-        bias = _f32c(bias, "bias")
-        if bias.numel() != N:
-            raise RuntimeError("mgnns::mm: bias has %d elements, expected %d" % (bias.numel(), N))
-    c = torch.empty((M, N), device=a.device, dtype=torch.float32)
-    gemm_raw(trans_a, trans_b, M, N, K, a, a.stride(0), 0, b, b.stride(0), 0, c, N, 0,
-             bias=bias, act=act, slope=slope)
+        if not (bias.is_cuda and bias.dtype is _f32 and bias.is_contiguous() and bias.numel() == N):
+            _need_cuda(bias)
+            bias = _f32c(bias, "bias")
+            if bias.numel() != N:
+                raise RuntimeError("mgnns::mm: bias has %d elements, expected %d" % (bias.numel(), N))
+        bp = bias.data_ptr()
+    c = torch.empty((M, N), device=a.device, dtype=_f32)
+    rc = _gemm(trans_a, trans_b, M, N, K, a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 0,
+               c.data_ptr(), N, 0, 1, 1, 0, bp, act, slope, _raw_stream(a.device.index))
+    if rc:
+        _check(rc, "gemm")
     return c
 
 
@@ -210,7 +252,7 @@ def _mm_backward(ctx, g):
     ta, tb, act, slope, has_bias = ctx.cfg
     g = act_bwd(y, g, act, slope) if act != ACT_NONE else _f32c(g, "grad")
     ga = gb = gbias = None
-    mm = torch.ops.mgnns.mm
+    mm = _mm_impl            # backward needs no autograd graph: skip the dispatcher
     if ctx.needs_input_grad[0]:
         ga = mm(g, b, None, False, not tb, ACT_NONE, 0.0) if not ta else mm(b, g, None, tb, True, ACT_NONE, 0.0)
     if ctx.needs_input_grad[1]:
@@ -477,7 +519,7 @@ def _attn_impl(u, bank, mask, scale, p_drop, seed):
     lse = torch.empty((B, H), device=u.device, dtype=torch.float32)
     with _timed("attn_q1_fwd"):
         _check(_lib.mgnns_attn_q1_fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale),
-                                      float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, ctx.data_ptr(), attn.data_ptr(),
+                                      float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), ctx.data_ptr(), attn.data_ptr(),
                                       psum.data_ptr(), lse.data_ptr(), _stream()), "attn_q1_fwd")
     return ctx, attn, psum, lse
 
@@ -511,7 +553,7 @@ def _attn_backward(ctx, g_ctx, g_attn, g_psum, g_lse):
     with _timed("attn_q1_bwd"):
         _check(_lib.mgnns_attn_q1_bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
                                       _ptr(g_psum), B, H, L, D, float(scale), float(p_drop),
-                                      seed & 0xFFFFFFFFFFFFFFFF, gu.data_ptr(), gbank.data_ptr(), _stream()),
+                                      seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), gu.data_ptr(), gbank.data_ptr(), _stream()),
                "attn_q1_bwd")
     return gu, gbank, None, None, None, None
 
@@ -538,7 +580,7 @@ def _label_impl(q, kv, heads, inv_scale, p_drop, seed):
     B, C = kv.shape[0], q.shape[0]
     out = torch.empty((B, C, HD), device=q.device, dtype=torch.float32)
     _check(_lib.mgnns_label_attn_fwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD, 2 * HD, B, C, heads,
-                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
+                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(),
                                      out.data_ptr(), _stream()), "label_attn_fwd")
     return out
 
@@ -566,7 +608,7 @@ def _label_backward(ctx, g):
     gq = torch.zeros_like(q)
     gkv = torch.empty_like(kv)
     _check(_lib.mgnns_label_attn_bwd(q.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD, 2 * HD, B, C, heads,
-                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF,
+                                     HD // heads, float(inv_scale), float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(),
                                      g.data_ptr(), gq.data_ptr(), gkv.data_ptr(), gkv.data_ptr() + 4 * HD, 2 * HD,
                                      _stream()), "label_attn_bwd")
     return gq, gkv, None, None, None, None
@@ -769,38 +811,72 @@ LSTM_TILE = 8
 
 class LstmPlan:
     """Host-side schedule for one batch of variable-length sequences (built from the CPU lengths the
-    reference already keeps on the host, engine:804 / model:376 — no device sync)."""
+    reference already keeps on the host, engine:804 / model:376 — no device sync).
 
-    def __init__(self, lens_cpu: torch.Tensor, L: int, device):
-        import numpy as np
-        lens = lens_cpu.detach().to('cpu', torch.int64).numpy()
-        lens = np.clip(lens, 0, L)
-        B = lens.shape[0]
-        offsets = np.zeros(B + 1, dtype=np.int64)
-        np.cumsum(lens, out=offsets[1:])
-        self.B, self.L, self.N = B, L, int(offsets[-1])
-        order = np.argsort(-lens, kind='stable')
-        order = order[lens[order] > 0]
-        n_tiles = (order.shape[0] + LSTM_TILE - 1) // LSTM_TILE
-        tiles = np.full(n_tiles * LSTM_TILE, -1, dtype=np.int64)
-        tiles[:order.shape[0]] = order
-        self.n_tiles = n_tiles
-        rows = np.repeat(np.arange(B, dtype=np.int64), lens)
-        pos = np.arange(self.N, dtype=np.int64) - offsets[rows]
-        flat = rows * L + pos
-        last = offsets[1:] - 1                      # compact row of each sequence's last token
-        packed = np.concatenate([offsets, lens, tiles]).astype(np.int32)
-        host = torch.from_numpy(packed).pin_memory() if torch.cuda.is_available() else torch.from_numpy(packed)
-        self.plan = host.to(device, non_blocking=True)
-        idx = torch.from_numpy(np.concatenate([flat, np.maximum(last, 0), offsets[:-1].clip(max=max(self.N - 1, 0))]))
-        idx = (idx.pin_memory() if torch.cuda.is_available() else idx).to(device, non_blocking=True)
-        self.flat_idx = idx[:self.N]                # compact row -> b*L + t
-        self.last_idx = idx[self.N:self.N + B]
-        self.first_idx = idx[self.N + B:]
+    Device tensors have a fixed `capacity` (compact rows, >= sum of lengths) so that the same plan object
+    can be refreshed in place with `update_()` between replays of a captured CUDA graph:
+      tok_idx  int64 [capacity]  compact row -> b*L + t           (padding rows -> 0)
+      flat_idx int64 [capacity]  compact row -> b*L + t           (padding rows -> B*L, a dummy bank row)
+      last_idx / first_idx int64 [B]  compact row of each sequence's last / first token
+      offsets int32 [B+1], lens int32 [B], tiles int32 [ceil(B/8)*8]
+    """
+
+    def __init__(self, lens_cpu: torch.Tensor, L: int, device, capacity=None):
+        self.B, self.L, self.device = int(lens_cpu.shape[0]), int(L), device
+        self.n_tiles = (self.B + LSTM_TILE - 1) // LSTM_TILE
+        packed, idx, n = self._host_arrays(lens_cpu, capacity)
+        self.capacity = int(idx.shape[0] - 2 * self.B) // 2
+        self.N = n
+        pin = torch.cuda.is_available()
+        self._host_plan = torch.from_numpy(packed).pin_memory() if pin else torch.from_numpy(packed)
+        self._host_idx = torch.from_numpy(idx).pin_memory() if pin else torch.from_numpy(idx)
+        self.plan = self._host_plan.to(device, non_blocking=True)
+        self.idx = self._host_idx.to(device, non_blocking=True)
+        B, cap = self.B, self.capacity
+        self.tok_idx = self.idx[:cap]
+        self.flat_idx = self.idx[cap:2 * cap]
+        self.last_idx = self.idx[2 * cap:2 * cap + B]
+        self.first_idx = self.idx[2 * cap + B:]
         self.offsets = self.plan[:B + 1]
         self.lens = self.plan[B + 1:2 * B + 1]
         self.tiles = self.plan[2 * B + 1:]
-        self.has_empty = bool((lens == 0).any())
+
+    def _host_arrays(self, lens_cpu, capacity):
+        import numpy as np
+        B, L = self.B, self.L
+        lens = np.clip(lens_cpu.detach().to('cpu', torch.int64).numpy(), 0, L)
+        offsets = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        n = int(offsets[-1])
+        cap = n if capacity is None else int(capacity)
+        if cap < n:
+            raise RuntimeError("LstmPlan: %d valid tokens exceed the plan capacity %d" % (n, cap))
+        order = np.argsort(-lens, kind='stable')
+        order = order[lens[order] > 0]
+        tiles = np.full(self.n_tiles * LSTM_TILE, -1, dtype=np.int64)
+        tiles[:order.shape[0]] = order
+        rows = np.repeat(np.arange(B, dtype=np.int64), lens)
+        flat = rows * L + (np.arange(n, dtype=np.int64) - offsets[rows])
+        tok = np.zeros(cap, dtype=np.int64)
+        tok[:n] = flat
+        flat_pad = np.full(cap, B * L, dtype=np.int64)
+        flat_pad[:n] = flat
+        hi = max(n - 1, 0)
+        last = np.clip(offsets[1:] - 1, 0, hi)
+        first = np.clip(offsets[:-1], 0, hi)
+        packed = np.concatenate([offsets, lens, tiles]).astype(np.int32)
+        idx = np.concatenate([tok, flat_pad, last, first])
+        return packed, idx, n
+
+    def update_(self, lens_cpu: torch.Tensor):
+        """Refresh the device tensors in place for a new batch (same B, L and capacity)."""
+        packed, idx, n = self._host_arrays(lens_cpu, self.capacity)
+        self.N = n
+        self._host_plan.copy_(torch.from_numpy(packed))
+        self._host_idx.copy_(torch.from_numpy(idx))
+        self.plan.copy_(self._host_plan, non_blocking=True)
+        self.idx.copy_(self._host_idx, non_blocking=True)
+        return self
 
 
 _LIB.define("lstm_rec(Tensor g, Tensor whh_f, Tensor whh_r, Tensor offsets, Tensor lens, Tensor tiles, int n_tiles) "
@@ -826,10 +902,12 @@ def _lstm_impl(g, whh_f, whh_r, offsets, lens, tiles, n_tiles):
     wt4 = torch.empty((2, H, H, 4), device=dev, dtype=torch.float32)
     _check(_lib.mgnns_lstm_prep_whh(whh_f.data_ptr(), wt4[0].data_ptr(), H, s), "lstm_prep_whh")
     _check(_lib.mgnns_lstm_prep_whh(whh_r.data_ptr(), wt4[1].data_ptr(), H, s), "lstm_prep_whh")
-    y = torch.empty((N, 2 * H), device=dev, dtype=torch.float32)
+    # rows beyond the valid tokens (plan capacity padding) are never written by the kernel: keep them zero so
+    # that the dense GEMMs downstream (next layer, weight gradients) see exact zeros there
+    y = torch.zeros((N, 2 * H), device=dev, dtype=torch.float32)
     gates = torch.empty((N, 2, 4, H), device=dev, dtype=torch.float32)
     csave = torch.empty((N, 2, H), device=dev, dtype=torch.float32)
-    hprev = torch.empty((N, 2, H), device=dev, dtype=torch.float32)
+    hprev = torch.zeros((N, 2, H), device=dev, dtype=torch.float32)
     with _timed("lstm_rec_fwd"):
         _check(_lib.mgnns_lstm_rec_fwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), n_tiles, H, g.data_ptr(),
                                        wt4[0].data_ptr(), wt4[1].data_ptr(), y.data_ptr(), gates.data_ptr(),
@@ -860,7 +938,7 @@ def _lstm_backward(ctx, gy, ggates, gc, ghp):
     H = whh_f.shape[1]
     gy = _f32c(gy, "grad_y")
     N = gy.shape[0]
-    dG = torch.empty((N, 8 * H), device=gy.device, dtype=torch.float32)
+    dG = torch.zeros((N, 8 * H), device=gy.device, dtype=torch.float32)
     with _timed("lstm_rec_bwd"):
         _check(_lib.mgnns_lstm_rec_bwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), ctx.n_tiles, H,
                                        gy.data_ptr(), gates.data_ptr(), csave.data_ptr(), whh_f.data_ptr(),
