@@ -61,6 +61,16 @@ int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
                    int batch, int reduce, int accumulate,
                    const float* bias, int act, float slope, void* stream);
 
+/* Single-pair variant with a caller-provided workspace: small products (fewer than 148 CTAs) are
+ * split along K into partial tiles in `workspace` and summed in a fixed order by a second kernel,
+ * so results stay bitwise run-to-run deterministic.  mgnns_gemm_splitk_workspace() returns the
+ * number of floats the split would need for a shape (0 = no split). */
+int64_t mgnns_gemm_splitk_workspace(int M, int N, int K);
+int mgnns_gemm_f32_ws(int transA, int transB, int M, int N, int K,
+                      const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                      const float* bias, int act, float slope, float* workspace, int64_t workspace_floats,
+                      void* stream);
+
 /* y = act'(y_saved) * g   (elementwise; backward of a fused activation) */
 int mgnns_act_bwd_f32(const float* y, const float* g, float* out, int64_t n,
                       int act, float slope, void* stream);

@@ -21,6 +21,9 @@ SIGNATURES = {
     "mgnns_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_int,
                                P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64,
                                c_int, c_int, c_int, P, c_int, c_float, P]),
+    "mgnns_gemm_splitk_workspace": (c_int64, [c_int, c_int, c_int]),
+    "mgnns_gemm_f32_ws": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, c_int64,
+                                  P, c_int, c_float, P, c_int64, P]),
     "mgnns_act_bwd_f32": (c_int, [P, P, P, c_int64, c_int, c_float, P]),
     "mgnns_colsum_f32": (c_int, [P, c_int64, c_int, c_int64, P, P]),
     "mgnns_spmm_csr_f32": (c_int, [c_int, P, P, P, P, c_int64, c_int64, P, c_int64, c_int64, c_int, c_int, P]),

@@ -20,6 +20,7 @@ struct GemmParams {
     int vecA, vecB, vecC;
     int ksplit;        // >1: grid.z splits K of a single (A,B) pair, partial tiles are atomically added into C
     int klen;          // K elements per split
+    float* ws;         // ksplit>1 && ws: partial tiles go to ws[z][M][N] (deterministic two-pass split-K)
 };
 
 constexpr int BK = 16;
@@ -150,8 +151,13 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
         __syncthreads();
     }
 
-    float* Cz = p.C + (p.ksplit > 1 ? 0 : (int64_t)z * p.strideC);
-    const bool add_bias = p.bias != nullptr && (p.ksplit <= 1 || z == 0);
+    const bool to_ws = p.ksplit > 1 && p.ws != nullptr;
+    float* Cz = to_ws ? p.ws + (int64_t)z * p.M * p.N : p.C + (p.ksplit > 1 ? 0 : (int64_t)z * p.strideC);
+    const int64_t ldc = to_ws ? p.N : p.ldc;
+    const bool add_bias = !to_ws && p.bias != nullptr && (p.ksplit <= 1 || z == 0);
+    const int act = to_ws ? MGNNS_ACT_NONE : p.act;
+    const int accumulate = to_ws ? 0 : p.accumulate;
+    const int vecC = to_ws ? ((p.N & 3) == 0) : p.vecC;
 #pragma unroll
     for (int gi = 0; gi < RM; ++gi)
 #pragma unroll
@@ -167,14 +173,14 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
                 for (int j = 0; j < 4; ++j) {
                     float x = acc[gi * 4 + i][gj * 4 + j];
                     if (add_bias && col + j < p.N) x += __ldg(p.bias + col + j);
-                    v[j] = apply_act(x, p.act, p.slope);
+                    v[j] = apply_act(x, act, p.slope);
                 }
-                float* dst = Cz + (int64_t)row * p.ldc + col;
-                if (p.accumulate) {
+                float* dst = Cz + (int64_t)row * ldc + col;
+                if (accumulate) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (col + j < p.N) atomicAdd(dst + j, v[j]);
-                } else if (p.vecC && col + 3 < p.N) {
+                } else if (vecC && col + 3 < p.N) {
                     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
 #pragma unroll
@@ -194,6 +200,19 @@ static int launch_gemm(const GemmParams& p, int transA, int transB, int nz, cuda
     else gemm_ffma_kernel<RM, RN, true, true><<<grid, 256, 0, st>>>(p);
     MG_LAUNCH_CHECK("gemm_ffma");
     return 0;
+}
+
+// second pass of the deterministic split-K: C = act(sum_z ws[z] + bias), fixed summation order
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C,
+                                     int64_t ldc, const float* __restrict__ bias, int act, float slope) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
+        float v = 0.f;
+        for (int z = 0; z < splits; ++z) v += ws[(int64_t)z * total + i];
+        if (bias != nullptr) v += __ldg(bias + n);
+        C[(int64_t)m * ldc + n] = apply_act(v, act, slope);
+    }
 }
 
 __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g,
@@ -234,12 +253,51 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t M, int N, int
 
 using namespace mgnns;
 
+static int gemm_impl(int transA, int transB, int M, int N, int K,
+                     const float* A, int64_t lda, int64_t strideA,
+                     const float* B, int64_t ldb, int64_t strideB,
+                     float* C, int64_t ldc, int64_t strideC,
+                     int batch, int reduce, int accumulate,
+                     const float* bias, int act, float slope, float* workspace, int64_t workspace_floats,
+                     void* stream);
+
 extern "C" int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
                               const float* A, int64_t lda, int64_t strideA,
                               const float* B, int64_t ldb, int64_t strideB,
                               float* C, int64_t ldc, int64_t strideC,
                               int batch, int reduce, int accumulate,
                               const float* bias, int act, float slope, void* stream) {
+    return gemm_impl(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, reduce,
+                     accumulate, bias, act, slope, nullptr, 0, stream);
+}
+
+// Same contraction for a single (A,B) pair with a caller-provided workspace: small products are split
+// along K into `workspace` partial tiles and summed in a fixed order (bitwise run-to-run deterministic).
+// mgnns_gemm_splitk_workspace() returns the number of floats needed (0 = no split will be used).
+extern "C" int64_t mgnns_gemm_splitk_workspace(int M, int N, int K) {
+    int64_t ctas = (int64_t)((M + 63) / 64) * ((N + 63) / 64);
+    if (ctas >= 148 || K < 128) return 0;
+    int split = (int)((148 * 2 + ctas - 1) / ctas);
+    if (split > K / 64) split = K / 64;
+    if (split > 8) split = 8;
+    return split > 1 ? (int64_t)split * M * N : 0;
+}
+
+extern "C" int mgnns_gemm_f32_ws(int transA, int transB, int M, int N, int K,
+                                 const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                                 const float* bias, int act, float slope, float* workspace, int64_t workspace_floats,
+                                 void* stream) {
+    return gemm_impl(transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, 1, 0, bias, act, slope, workspace,
+                     workspace_floats, stream);
+}
+
+static int gemm_impl(int transA, int transB, int M, int N, int K,
+                     const float* A, int64_t lda, int64_t strideA,
+                     const float* B, int64_t ldb, int64_t strideB,
+                     float* C, int64_t ldc, int64_t strideC,
+                     int batch, int reduce, int accumulate,
+                     const float* bias, int act, float slope, float* workspace, int64_t workspace_floats,
+                     void* stream) {
     MG_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "gemm: negative dimension");
     MG_REQUIRE(reduce >= 1 && (batch % reduce) == 0, "gemm: batch (%d) must be a multiple of reduce (%d)", batch, reduce);
     MG_REQUIRE(!(accumulate && (bias != nullptr || act != MGNNS_ACT_NONE)), "gemm: accumulate excludes bias/activation");
@@ -260,6 +318,26 @@ extern "C" int mgnns_gemm_f32(int transA, int transB, int M, int N, int K,
     cudaStream_t st = as_stream(stream);
     p.ksplit = 1;
     p.klen = K;
+    p.ws = nullptr;
+    // deterministic two-pass split-K into the caller's workspace
+    if (workspace != nullptr && batch == 1 && !accumulate) {
+        const int64_t need = mgnns_gemm_splitk_workspace(M, N, K);
+        if (need > 0 && need <= workspace_floats) {
+            int split = (int)(need / ((int64_t)M * N));
+            int klen = ((K + split - 1) / split + BK - 1) / BK * BK;
+            split = (K + klen - 1) / klen;
+            p.ksplit = split;
+            p.klen = klen;
+            p.ws = workspace;
+            if (int rc = launch_gemm<1, 1>(p, transA, transB, split, st)) return rc;
+            int64_t total = (int64_t)M * N;
+            int blocks = (int)((total + 255) / 256);
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            splitk_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, split, M, N, C, ldc, bias, act, slope);
+            MG_LAUNCH_CHECK("splitk_reduce");
+            return 0;
+        }
+    }
     // big tiles only when they still fill the machine
     int64_t big_ctas = (int64_t)((M + 127) / 128) * ((N + 127) / 128) * nz;
     if (big_ctas >= 148 * 2) return launch_gemm<2, 2>(p, transA, transB, nz, st);

@@ -221,6 +221,258 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
     }
 }
 
+
+// =====================================================================================================
+// Cluster variant: a pair of CTAs (thread-block cluster of 2, distributed shared memory) owns one
+// (tile, direction).  Each CTA keeps HALF of W_hh resident in shared memory for the whole kernel
+// (forward: the gate columns of its H/2 hidden units, 180 KB at H=150; backward: the matching H/2
+// columns of W_hh), so the per-step weight traffic comes from shared memory instead of L2, and the two
+// CTAs exchange only the new hidden state (forward) / gate gradients (backward) through DSMEM stores
+// followed by one cluster barrier.
+// =====================================================================================================
+constexpr int CL_THREADS = 320;
+
+__device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cl_map(const void* p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_store(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
+    LstmPlan plan, const float* __restrict__ G, const float* __restrict__ wt_f, const float* __restrict__ wt_r,
+    float* __restrict__ Y, float* __restrict__ gates, float* __restrict__ csave, float* __restrict__ hprev) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = plan.H, Hh = H / 2, NC = 4 * Hh;          // NC = gate columns owned by this CTA
+    float* Wsm = sm;                                         // [H][NC]
+    float* hs = Wsm + H * NC;                                // [2][H][TS]
+    float* zp = hs + 2 * H * TS;                             // [2 k-halves][TS][NC]
+    __shared__ int s_off[TS], s_len[TS];
+    const int dir = blockIdx.y, tile = blockIdx.x >> 1;
+    const uint32_t rank = cl_rank(), peer = rank ^ 1u;
+    const float* __restrict__ WT = dir ? wt_r : wt_f;        // [H][4H]
+    const int tid = threadIdx.x;
+    if (tid < TS) {
+        int s = plan.tiles[tile * TS + tid];
+        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
+    }
+    for (int i = tid; i < H * NC; i += CL_THREADS) {
+        const int k = i / NC, lc = i - k * NC, g = lc / Hh, uu = lc - g * Hh;
+        Wsm[i] = WT[(int64_t)k * (4 * H) + g * H + rank * Hh + uu];
+    }
+    for (int i = tid; i < 2 * H * TS; i += CL_THREADS) hs[i] = 0.f;
+    __syncthreads();
+    int tile_len = 0;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
+    cl_sync();                                               // peer's buffers are initialised before any remote store
+
+    // z-phase mapping: two groups of 160 threads split the k range; each thread owns two columns
+    const int grp = tid / 160, jl = tid % 160;
+    const bool zlive = jl < NC / 2;
+    const int k_lo = grp ? H / 2 : 0, k_hi = grp ? H : H / 2;
+    // activation mapping: pairs (unit, sequence); at most two per thread, fixed for the whole kernel
+    const int npairs = Hh * TS;
+    int p_s[2], p_u[2];
+    bool p_ok[2];
+    float cst[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int p = tid + q * CL_THREADS;
+        p_ok[q] = p < npairs;
+        p_s[q] = p_ok[q] ? p / Hh : 0;
+        p_u[q] = p_ok[q] ? p % Hh : 0;
+    }
+    int cur = 0;
+    for (int t = 0; t < tile_len; ++t) {
+        // prefetch this step's input projections while the recurrent product runs
+        float gin[2][4];
+        int64_t rowq[2];
+        bool act[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int len = s_len[p_s[q]];
+            act[q] = p_ok[q] && t < len;
+            rowq[q] = 0;
+            if (act[q]) {
+                const int tt = dir ? (len - 1 - t) : t;
+                rowq[q] = s_off[p_s[q]] + tt;
+                const float* g_in = G + rowq[q] * (8 * H) + dir * 4 * H + rank * Hh + p_u[q];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) gin[q][g] = __ldg(g_in + g * H);
+            }
+        }
+        if (zlive) {
+            float a0[TS], a1[TS];
+#pragma unroll
+            for (int s = 0; s < TS; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+            const float* hcur = hs + cur * H * TS;
+#pragma unroll 5
+            for (int k = k_lo; k < k_hi; ++k) {
+                const float w0 = Wsm[k * NC + jl], w1 = Wsm[k * NC + NC / 2 + jl];
+                const float4 h0 = *reinterpret_cast<const float4*>(hcur + k * TS);
+                const float4 h1 = *reinterpret_cast<const float4*>(hcur + k * TS + 4);
+                a0[0] = fmaf(w0, h0.x, a0[0]); a0[1] = fmaf(w0, h0.y, a0[1]); a0[2] = fmaf(w0, h0.z, a0[2]); a0[3] = fmaf(w0, h0.w, a0[3]);
+                a0[4] = fmaf(w0, h1.x, a0[4]); a0[5] = fmaf(w0, h1.y, a0[5]); a0[6] = fmaf(w0, h1.z, a0[6]); a0[7] = fmaf(w0, h1.w, a0[7]);
+                a1[0] = fmaf(w1, h0.x, a1[0]); a1[1] = fmaf(w1, h0.y, a1[1]); a1[2] = fmaf(w1, h0.z, a1[2]); a1[3] = fmaf(w1, h0.w, a1[3]);
+                a1[4] = fmaf(w1, h1.x, a1[4]); a1[5] = fmaf(w1, h1.y, a1[5]); a1[6] = fmaf(w1, h1.z, a1[6]); a1[7] = fmaf(w1, h1.w, a1[7]);
+            }
+            float* z = zp + grp * TS * NC;
+#pragma unroll
+            for (int s = 0; s < TS; ++s) { z[s * NC + jl] = a0[s]; z[s * NC + NC / 2 + jl] = a1[s]; }
+        }
+        __syncthreads();
+        float* hnext = hs + (cur ^ 1) * H * TS;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!p_ok[q]) continue;
+            const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
+            const float hold = hs[cur * H * TS + u * TS + s];
+            float hnew = hold;
+            if (act[q]) {
+                const float* z0 = zp + s * NC;
+                const float* z1 = zp + TS * NC + s * NC;
+                const float ig = sigmoidf_(z0[uu] + z1[uu] + gin[q][0]);
+                const float fg = sigmoidf_(z0[Hh + uu] + z1[Hh + uu] + gin[q][1]);
+                const float gg = tanhf_(z0[2 * Hh + uu] + z1[2 * Hh + uu] + gin[q][2]);
+                const float og = sigmoidf_(z0[3 * Hh + uu] + z1[3 * Hh + uu] + gin[q][3]);
+                cst[q] = fg * cst[q] + ig * gg;
+                hnew = og * tanhf_(cst[q]);
+                const int64_t row = rowq[q];
+                Y[row * (2 * H) + dir * H + u] = hnew;
+                float* gs = gates + (row * 2 + dir) * (4 * H);
+                gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
+                csave[(row * 2 + dir) * H + u] = cst[q];
+                hprev[(row * 2 + dir) * H + u] = hold;
+            }
+            hnext[u * TS + s] = hnew;
+            cl_store(cl_map(hnext + u * TS + s, peer), hnew);
+        }
+        cl_sync();
+        cur ^= 1;
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_bwd_cl_kernel(
+    LstmPlan plan, const float* __restrict__ dY, const float* __restrict__ gates, const float* __restrict__ csave,
+    const float* __restrict__ whh_f, const float* __restrict__ whh_r, float* __restrict__ dG) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = plan.H, Hh = H / 2;
+    float* Wb = sm;                                          // [4H][Hh]: W_hh columns of this CTA's hidden units
+    float* dzs = Wb + 4 * H * Hh;                            // [4H][TS]
+    float* part = dzs + 4 * H * TS;                          // [4][TS][Hh]
+    float* dh = part + 4 * TS * Hh;                          // [TS][Hh]
+    __shared__ int s_off[TS], s_len[TS];
+    const int dir = blockIdx.y, tile = blockIdx.x >> 1;
+    const uint32_t rank = cl_rank(), peer = rank ^ 1u;
+    const float* __restrict__ W = dir ? whh_r : whh_f;       // [4H][H]
+    const int tid = threadIdx.x;
+    if (tid < TS) {
+        int s = plan.tiles[tile * TS + tid];
+        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
+    }
+    for (int i = tid; i < 4 * H * Hh; i += CL_THREADS) {
+        const int j = i / Hh, kk = i - j * Hh;
+        Wb[i] = W[(int64_t)j * H + rank * Hh + kk];
+    }
+    for (int i = tid; i < TS * Hh; i += CL_THREADS) dh[i] = 0.f;
+    __syncthreads();
+    int tile_len = 0;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
+    cl_sync();
+
+    const int npairs = Hh * TS;
+    int p_s[2], p_u[2];
+    bool p_ok[2];
+    float dcs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int p = tid + q * CL_THREADS;
+        p_ok[q] = p < npairs;
+        p_s[q] = p_ok[q] ? p / Hh : 0;
+        p_u[q] = p_ok[q] ? p % Hh : 0;
+    }
+    // phase-2 mapping: thread (kk, quarter of the 4H gate rows)
+    const int kk2 = tid % 80, jq = tid / 80;
+    const bool live2 = kk2 < Hh;
+    for (int t = tile_len - 1; t >= 0; --t) {
+        // ---- phase 1: gate gradients for this CTA's hidden units -------------------------------------
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!p_ok[q]) continue;
+            const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
+            const int len = s_len[s];
+            float dz[4] = {0.f, 0.f, 0.f, 0.f};
+            if (t < len) {
+                const int tt = dir ? (len - 1 - t) : t;
+                const int64_t row = s_off[s] + tt;
+                const float* gs = gates + (row * 2 + dir) * (4 * H);
+                const float ig = gs[u], fg = gs[H + u], gg = gs[2 * H + u], og = gs[3 * H + u];
+                const float c = csave[(row * 2 + dir) * H + u];
+                float cprev = 0.f;
+                if (t > 0) {
+                    const int64_t rp = dir ? row + 1 : row - 1;
+                    cprev = csave[(rp * 2 + dir) * H + u];
+                }
+                const float dhv = dY[row * (2 * H) + dir * H + u] + dh[s * Hh + uu];
+                const float tc = tanhf_(c);
+                const float dct = dcs[q] + dhv * og * (1.f - tc * tc);
+                dz[0] = dct * gg * ig * (1.f - ig);
+                dz[1] = dct * cprev * fg * (1.f - fg);
+                dz[2] = dct * ig * (1.f - gg * gg);
+                dz[3] = dhv * tc * og * (1.f - og);
+                dcs[q] = dct * fg;
+                float* out = dG + row * (8 * H) + dir * 4 * H;
+                out[u] = dz[0]; out[H + u] = dz[1]; out[2 * H + u] = dz[2]; out[3 * H + u] = dz[3];
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float* slot = dzs + (g * H + u) * TS + s;
+                *slot = dz[g];
+                cl_store(cl_map(slot, peer), dz[g]);
+            }
+        }
+        cl_sync();
+        // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
+        if (t > 0) {
+            float acc[TS];
+#pragma unroll
+            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+            if (live2) {
+                const int j0 = jq * H;
+#pragma unroll 5
+                for (int j = 0; j < H; ++j) {
+                    const float w = Wb[(j0 + j) * Hh + kk2];
+                    const float4 d0 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS);
+                    const float4 d1 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS + 4);
+                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
+                    acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
+                    acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                }
+#pragma unroll
+                for (int s = 0; s < TS; ++s) part[(jq * TS + s) * Hh + kk2] = acc[s];
+            }
+            __syncthreads();
+            for (int i = tid; i < TS * Hh; i += CL_THREADS)
+                dh[i] = part[i] + part[TS * Hh + i] + part[2 * TS * Hh + i] + part[3 * TS * Hh + i];
+        }
+        cl_sync();      // dzs may be overwritten (also remotely) by the next step only after both CTAs finished phase 2
+    }
+}
+
+static size_t lstm_cl_fwd_smem(int H) { return sizeof(float) * ((size_t)H * 2 * H + 2 * H * TS + 2 * TS * 2 * H); }
+static size_t lstm_cl_bwd_smem(int H) { return sizeof(float) * ((size_t)4 * H * (H / 2) + 4 * H * TS + 4 * TS * (H / 2) + TS * (H / 2)); }
+
 }  // namespace mgnns
 
 using namespace mgnns;
@@ -242,6 +494,19 @@ extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, c
     if (n_tiles == 0) return 0;
     MG_REQUIRE(offsets && lens && tiles && G && wt4_f && wt4_r && Y && gates && csave && hprev, "lstm_rec_fwd: null pointer");
     LstmPlan plan{offsets, lens, tiles, H};
+    const size_t smem = lstm_cl_fwd_smem(H);
+    if (smem <= 225 * 1024 && H <= 2 * 80) {
+        // cluster-of-2 variant with W_hh resident in (distributed) shared memory
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(lstm_rec_fwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            MG_REQUIRE(e == cudaSuccess, "lstm_rec_fwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
+            configured = true;
+        }
+        lstm_rec_fwd_cl_kernel<<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+        MG_LAUNCH_CHECK("lstm_rec_fwd_cl");
+        return 0;
+    }
     lstm_rec_fwd_kernel<<<dim3(n_tiles, 2), LSTM_THREADS, 0, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
     MG_LAUNCH_CHECK("lstm_rec_fwd");
     return 0;
@@ -254,6 +519,18 @@ extern "C" int mgnns_lstm_rec_bwd(const int32_t* offsets, const int32_t* lens, c
     if (n_tiles == 0) return 0;
     MG_REQUIRE(offsets && lens && tiles && dY && gates && csave && whh_f && whh_r && dG, "lstm_rec_bwd: null pointer");
     LstmPlan plan{offsets, lens, tiles, H};
+    const size_t smem = lstm_cl_bwd_smem(H);
+    if (smem <= 225 * 1024 && H <= 2 * 80) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(lstm_rec_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            MG_REQUIRE(e == cudaSuccess, "lstm_rec_bwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
+            configured = true;
+        }
+        lstm_rec_bwd_cl_kernel<<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+        MG_LAUNCH_CHECK("lstm_rec_bwd_cl");
+        return 0;
+    }
     lstm_rec_bwd_kernel<<<dim3(n_tiles, 2), LSTM_THREADS, 0, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
     MG_LAUNCH_CHECK("lstm_rec_bwd");
     return 0;

@@ -175,7 +175,17 @@ def _mm_shapes(a, b, trans_a, trans_b):
 
 
 _gemm = _lib.mgnns_gemm_f32
+_gemm_ws = _lib.mgnns_gemm_f32_ws
 _f32 = torch.float32
+_ws_cache = {}
+
+
+def _ws_size(M, N, K):
+    key = (M, N, K)
+    v = _ws_cache.get(key)
+    if v is None:
+        v = _ws_cache[key] = int(_lib.mgnns_gemm_splitk_workspace(M, N, K))
+    return v
 
 
 def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
@@ -206,8 +216,15 @@ def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
                 raise RuntimeError("mgnns::mm: bias has %d elements, expected %d" % (bias.numel(), N))
         bp = bias.data_ptr()
     c = torch.empty((M, N), device=a.device, dtype=_f32)
-    rc = _gemm(trans_a, trans_b, M, N, K, a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 0,
-               c.data_ptr(), N, 0, 1, 1, 0, bp, act, slope, _raw_stream(a.device.index))
+    ws_floats = 0 if trans_a else _ws_size(M, N, K)
+    if ws_floats:
+        # small forward-shaped product: deterministic two-pass split-K through a scratch buffer
+        ws = torch.empty((ws_floats,), device=a.device, dtype=_f32)
+        rc = _gemm_ws(trans_a, trans_b, M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                      c.data_ptr(), N, bp, act, slope, ws.data_ptr(), ws_floats, _raw_stream(a.device.index))
+    else:
+        rc = _gemm(trans_a, trans_b, M, N, K, a.data_ptr(), a.stride(0), 0, b.data_ptr(), b.stride(0), 0,
+                   c.data_ptr(), N, 0, 1, 1, 0, bp, act, slope, _raw_stream(a.device.index))
     if rc:
         _check(rc, "gemm")
     return c
