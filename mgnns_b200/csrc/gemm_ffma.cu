@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z;
 
-    const int kbase = p.ksplit > 1 ? z * p.klen : 0;
+    const int zsplit = p.ksplit > 1 ? z % p.ksplit : 0;       // K slice
+    const int zpair = p.ksplit > 1 ? z / p.ksplit : z;          // (A,B) pair / output index
+    const int kbase = p.ksplit > 1 ? zsplit * p.klen : 0;
     const int kend = p.ksplit > 1 ? min(p.K, kbase + p.klen) : p.K;
     const int ktiles = (kend - kbase + BK - 1) / BK;
     const int total = ktiles * p.reduce;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     float4 ra[NLA], rb[NLB];
     auto fetch = [&](int t) {
         int r = t / ktiles, kt = t - r * ktiles;
-        int64_t pair = p.ksplit > 1 ? 0 : (int64_t)z * p.reduce + r;
+        int64_t pair = p.ksplit > 1 ? zpair : (int64_t)z * p.reduce + r;
         // A is indexed by (m, k): TA means stored [k][m]
         load_tile<BM, TA, NLA>(ra, p.A + pair * p.strideA, p.lda, m0, kbase + kt * BK, p.M, kend, p.vecA, tid);
         // B is indexed by (k, n): stored [k][n] (n contiguous) unless TB
@@ -152,9 +154,9 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     }
 
     const bool to_ws = p.ksplit > 1 && p.ws != nullptr;
-    float* Cz = to_ws ? p.ws + (int64_t)z * p.M * p.N : p.C + (p.ksplit > 1 ? 0 : (int64_t)z * p.strideC);
+    float* Cz = to_ws ? p.ws + (int64_t)z * p.M * p.N : p.C + (int64_t)zpair * p.strideC;
     const int64_t ldc = to_ws ? p.N : p.ldc;
-    const bool add_bias = !to_ws && p.bias != nullptr && (p.ksplit <= 1 || z == 0);
+    const bool add_bias = !to_ws && p.bias != nullptr && (p.ksplit <= 1 || zsplit == 0);
     const int act = to_ws ? MGNNS_ACT_NONE : p.act;
     const int accumulate = to_ws ? 0 : p.accumulate;
     const int vecC = to_ws ? ((p.N & 3) == 0) : p.vecC;
@@ -345,7 +347,7 @@ static int gemm_impl(int transA, int transB, int M, int N, int K,
     // grid.z so that more than a handful of SMs work on it; partial tiles are summed with atomics
     int64_t ctas = (int64_t)((M + 63) / 64) * ((N + 63) / 64) * nz;
     // (only for the weight-gradient shape, transA: forward products stay bitwise run-to-run deterministic)
-    if (transA && batch == 1 && !accumulate && act == MGNNS_ACT_NONE && ctas < 148 && K >= 128) {
+    if (transA && reduce == 1 && !accumulate && act == MGNNS_ACT_NONE && ctas < 148 && K >= 128) {
         int split = (int)((148 * 2 + ctas - 1) / ctas);
         int max_split = K / 64;
         if (split > max_split) split = max_split;
@@ -353,12 +355,15 @@ static int gemm_impl(int transA, int transB, int M, int N, int K,
         if (split > 1) {
             int klen = ((K + split - 1) / split + BK - 1) / BK * BK;
             split = (K + klen - 1) / klen;
-            cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
-            MG_REQUIRE(e == cudaSuccess, "gemm: memset failed: %s", cudaGetErrorString(e));
+            for (int b = 0; b < batch; ++b) {
+                cudaError_t e = cudaMemset2DAsync(C + (int64_t)b * strideC, (size_t)ldc * sizeof(float), 0,
+                                                  (size_t)N * sizeof(float), (size_t)M, st);
+                MG_REQUIRE(e == cudaSuccess, "gemm: memset failed: %s", cudaGetErrorString(e));
+            }
             p.ksplit = split;
             p.klen = klen;
             p.accumulate = 1;
-            nz = split;
+            nz = split * batch;
         }
     }
     return launch_gemm<1, 1>(p, transA, transB, nz, st);
