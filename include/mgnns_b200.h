@@ -180,6 +180,21 @@ int mgnns_rowmax_bwd_f32(const float* grad_pooled, const int32_t* argmax, int64_
                          float* grad_F, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Dense layer on the tcgen05 tensor cores (TMA-fed, double-buffered TMEM accumulators):
+ *   C[M,N] = act(A[M,K] . W + bias)        A row-major (lda), C row-major (ldc)
+ *   w_is_kn: 1 = W is [K,N] (GraphConvolution layout), 0 = W is [N,K] (nn.Linear layout)
+ *   precision: 0 = TF32 operands, 1 = 3xTF32 split (fp32-class accuracy; needs
+ *              mgnns_linear_tc_workspace() floats of 16-byte aligned workspace for the split weight)
+ *   constraints: lda % 4 == 0, ldw % 4 == 0, A and W 16-byte aligned
+ * ref: support = torch.matmul(input, weight) + the activation applied by the caller,
+ *      models/Multi_GCN_Multihead_att.py:52-58, :470-472; nn.Linear call sites with many rows
+ * ------------------------------------------------------------------------- */
+int64_t mgnns_linear_tc_workspace(int N, int K, int64_t ldw, int w_is_kn, int precision);
+int mgnns_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, int w_is_kn,
+                    const float* bias, int act, float slope, int M, int N, int K, int precision,
+                    float* workspace, int64_t workspace_floats, float* C, int64_t ldc, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Image-bank contraction on the tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  *   fwd: bank[b,p,o] = sum_c fmap[b,c,p] * weight[o,c] + bias[o]
  *   dw : gW[o,c]    += sum_{b,p} gbank[b,p,o] * fmap[b,c,p]      (gW initialised by the caller)

@@ -8,8 +8,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_ffma.cu", "spmm.cu", "text_gcn.cu", "attention.cu", "small_ops.cu", "tc_gemm.cu", "lstm.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "mgnns_b200.h")]
+SOURCES = ["gemm_ffma.cu", "spmm.cu", "text_gcn.cu", "attention.cu", "small_ops.cu", "tc_gemm.cu", "tc_linear.cu", "lstm.cu"]
+HEADERS = ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "mgnns_b200.h")]
 LIB = os.path.join(HERE, "libmgnns_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 NVCC_FLAGS = [

@@ -175,6 +175,9 @@ def _mm_shapes(a, b, trans_a, trans_b):
 
 
 _gemm = _lib.mgnns_gemm_f32
+_linear_tc = _lib.mgnns_linear_tc
+_linear_tc_ws = _lib.mgnns_linear_tc_workspace
+_TC_MIN_ROWS = int(os.environ.get("MGNNS_TC_MIN_ROWS", "2048"))   # below this the 128-row tiles cannot fill 148 SMs
 _gemm_ws = _lib.mgnns_gemm_f32_ws
 _f32 = torch.float32
 _ws_cache = {}
@@ -216,6 +219,20 @@ def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
                 raise RuntimeError("mgnns::mm: bias has %d elements, expected %d" % (bias.numel(), N))
         bp = bias.data_ptr()
     c = torch.empty((M, N), device=a.device, dtype=_f32)
+    prec = _PRECISIONS[_precision]
+    if (prec is not None and not trans_a and M >= _TC_MIN_ROWS and a.stride(0) % 4 == 0 and b.stride(0) % 4 == 0
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        # many-row product: tcgen05 tensor cores (TMA-fed, TMEM accumulators), TF32 or 3xTF32 operands
+        w_is_kn = 0 if trans_b else 1
+        ldw = b.stride(0)
+        wsf = int(_linear_tc_ws(N, K, ldw, w_is_kn, prec))
+        ws = torch.empty((max(wsf, 4),), device=a.device, dtype=_f32)
+        with _timed("linear_tc"):
+            rc = _linear_tc(a.data_ptr(), a.stride(0), b.data_ptr(), ldw, w_is_kn, bp, act, slope, M, N, K, prec,
+                            ws.data_ptr(), wsf, c.data_ptr(), N, _raw_stream(a.device.index))
+        if rc:
+            _check(rc, "linear_tc")
+        return c
     ws_floats = 0 if trans_a else _ws_size(M, N, K)
     if ws_floats:
         # small forward-shaped product: deterministic two-pass split-K through a scratch buffer

@@ -142,3 +142,23 @@ def fill_parameters(module_or_dict, seed=0, scale=None):
     if not isinstance(module_or_dict, dict) and hasattr(module_or_dict, 'embedding'):
         with torch.no_grad():
             module_or_dict.embedding.weight[0].zero_()
+
+
+def cfg2_word_graph(N=10000, mean_degree=64, seed=0):
+    """SURVEY §8d cfg 2 adjacency: PMI-like word graph in CSR — power-law out-degrees (mean ~`mean_degree`
+    draws + a self loop, duplicates merged), neighbours drawn from a heavy-tailed popularity law, rows
+    normalised to sum 1.  Returns host arrays (rowptr int64 [N+1], col int64 [nnz], val float32 [nnz])."""
+    rs = np.random.RandomState(seed)
+    deg = np.clip((rs.pareto(1.3, N) + 1) * 20, 1, 3000).astype(np.int64)
+    deg = np.maximum(1, (deg * (float(mean_degree) * N / deg.sum())).astype(np.int64))
+    pop = (rs.pareto(1.1, N) + 1)
+    pop /= pop.sum()
+    rows, cols = [], []
+    for i in range(N):
+        c = np.unique(np.concatenate([rs.choice(N, deg[i], p=pop), [i]]))
+        rows.append(np.full(c.shape, i))
+        cols.append(c)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=N))])
+    val = (1.0 / np.diff(rowptr))[rows].astype(np.float32)
+    return rowptr, cols, val

@@ -443,6 +443,52 @@ def _imgbank_case(dev, B, rtol, atol):
     close(fg.grad, fd.grad, 1e-4, 1e-4)
 
 
+# ------------------------------------------------------------------------------------------- tensor-core dense layer
+@pytest.mark.parametrize("mode,rtol,atol", [("tf32x3", 5e-5, 3e-6), ("tf32", 5e-3, 1e-3)])
+@pytest.mark.parametrize("w_kn", [True, False])
+@pytest.mark.parametrize("M,N,K", [(2048, 512, 300), (2500, 300, 128), (4099, 1200, 300), (2304, 44, 36), (3000, 520, 2048)])
+def test_linear_tc_matches_fp64(dev, ops, mode, rtol, atol, w_kn, M, N, K):
+    """mgnns::mm routes products with >= 2048 rows to the tcgen05 kernel (ref: the X.W of
+    GraphConvolution.forward, model:53, fused with bias + activation)."""
+    prev = ops.set_precision(mode)
+    try:
+        a = rnd(M, K, seed=1)
+        w = rnd(K, N, seed=2) if w_kn else rnd(N, K, seed=2)
+        bias = rnd(N, seed=3)
+        ref = a.double() @ (w.double() if w_kn else w.double().t()) + bias.double()
+        before = ops.KernelTimers.records.get("linear_tc")
+        ops.KernelTimers.reset(["linear_tc"])
+        out = torch.ops.mgnns.mm(a.to(dev), w.to(dev), bias.to(dev), False, not w_kn, ops.ACT_NONE, 0.0)
+        assert len(ops.KernelTimers.records["linear_tc"]) == 1, "tensor-core path was not taken"
+        ops.KernelTimers.reset([])
+        # the TMEM accumulator truncates (round toward zero) on every add: the bound grows with K, not sqrt(K)
+        close(out, ref, rtol=rtol, atol=atol * K)
+        out = torch.ops.mgnns.mm(a.to(dev), w.to(dev), None, False, not w_kn, ops.ACT_RELU, 0.0)
+        close(out, torch.relu(ref - bias.double()), rtol=rtol, atol=atol * K)
+        out = torch.ops.mgnns.mm(a.to(dev), w.to(dev), bias.to(dev), False, not w_kn, ops.ACT_LEAKY, 0.2)
+        close(out, torch.nn.functional.leaky_relu(ref, 0.2), rtol=rtol, atol=atol * K)
+    finally:
+        ops.set_precision(prev)
+
+
+def test_linear_tc_fp32_mode_keeps_cuda_core_path_and_autograd(dev, ops):
+    a = rnd(2100, 300, seed=5).to(dev).requires_grad_()
+    w = rnd(300, 512, seed=6, scale=0.05).to(dev).requires_grad_()
+    prev = ops.set_precision("fp32")
+    try:
+        y32 = torch.ops.mgnns.mm(a, w, None, False, False, ops.ACT_RELU, 0.0)
+    finally:
+        ops.set_precision(prev)
+    y = torch.ops.mgnns.mm(a, w, None, False, False, ops.ACT_RELU, 0.0)       # default mode: tf32x3 on tensor cores
+    close(y, y32, 2e-5, 2e-5)
+    r = rnd(2100, 512, seed=7).to(dev)
+    (y * r).sum().backward()
+    ad, wd = a.detach().double().cpu().requires_grad_(), w.detach().double().cpu().requires_grad_()
+    (torch.relu(ad @ wd) * r.double().cpu()).sum().backward()
+    close(a.grad, ad.grad, 1e-4, 1e-4)
+    close(w.grad, wd.grad, 1e-4, 1e-3)
+
+
 # ------------------------------------------------------------------------------------------- PMI
 KAT_VOCAB = ['PAD', 'UNK', 'a', 'b', 'c', 'd', 'e']
 KAT_DOCS = ["a b c a d", "b c d e", "a a b zzz c", "e d c b a b c"]
