@@ -300,6 +300,59 @@ __global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ F
     }
 }
 
+// Vectorised variant for P % 4 == 0 rows (14x14 = 196): one warp per row, NV4 128-bit loads per lane, the row
+// maximum through one integer redux (order-preserving float->uint map), then the first position that attains it
+// through a second redux.  Same tie-breaking (lowest index) and NaN rule (a NaN wins, first NaN's index) as above.
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(256) rowmax_vec_kernel(const float* __restrict__ F, int64_t rows, int P,
+                                                         float* __restrict__ pooled, int32_t* __restrict__ argmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float4* row = reinterpret_cast<const float4*>(F + r * P);
+    const int n4 = P >> 2;
+    float v[4 * NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int q = lane + 32 * i;
+        float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (q < n4) x = __ldcs(row + q);                 // streamed: the image-bank GEMM re-reads the map from HBM anyway
+        v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
+    float m = -INFINITY;
+    bool has_nan = false;
+#pragma unroll
+    for (int j = 0; j < 4 * NV4; ++j) {
+        m = fmaxf(m, v[j]);                               // ignores NaN
+        has_nan |= (v[j] != v[j]);
+    }
+    const float best = ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(m)));
+    const bool any_nan = __ballot_sync(0xffffffffu, has_nan) != 0u;
+    uint32_t pos = 0xffffffffu;
+#pragma unroll
+    for (int i = NV4 - 1; i >= 0; --i)
+#pragma unroll
+        for (int e = 3; e >= 0; --e) {
+            const float x = v[4 * i + e];
+            const uint32_t p = 4u * (uint32_t)(lane + 32 * i) + (uint32_t)e;
+            const bool hit = any_nan ? (x != x) : (x == best);
+            if (hit && (lane + 32 * i) < n4) pos = p;    // descending scan: the lowest position is written last
+        }
+    pos = __reduce_min_sync(0xffffffffu, pos);
+    if (lane == 0) {
+        pooled[r] = any_nan ? __int_as_float(0x7fc00000) : best;
+        if (argmax) argmax[r] = (int32_t)pos;
+    }
+}
+
 __global__ void rowmax_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ argmax,
                                   int64_t rows, int P, float* __restrict__ gF) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,7 +469,16 @@ extern "C" int mgnns_rowmax_f32(const float* F, int64_t rows, int P, float* pool
     MG_REQUIRE(F && pooled, "rowmax: null pointer");
     int64_t blocks = (rows + 7) / 8;
     MG_REQUIRE(blocks < (1LL << 31), "rowmax: too many rows");
-    rowmax_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(F, rows, P, pooled, argmax);
+    const int nv4 = (P / 4 + 31) / 32;
+    if ((P & 3) == 0 && aligned16(F) && nv4 <= 4) {
+        cudaStream_t st = as_stream(stream);
+        if (nv4 == 1) rowmax_vec_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(F, rows, P, pooled, argmax);
+        else if (nv4 == 2) rowmax_vec_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(F, rows, P, pooled, argmax);
+        else if (nv4 == 3) rowmax_vec_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(F, rows, P, pooled, argmax);
+        else rowmax_vec_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(F, rows, P, pooled, argmax);
+    } else {
+        rowmax_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(F, rows, P, pooled, argmax);
+    }
     MG_LAUNCH_CHECK("rowmax");
     return 0;
 }

@@ -51,20 +51,22 @@ class GraphedTrainStep:
             ops.KernelTimers.enabled = timers
 
     def _allreduce(self):
+        """One flat NCCL all-reduce of every gradient (SUM, then / world).  Gradients are packed with one
+        multi-tensor copy; afterwards each p.grad aliases its slice of the flat buffer (no copy back), which is
+        what clip_grad_norm_ and the optimizer then read."""
         params = [p for p in self.model.parameters() if p.grad is not None]
         if self._flat is None:
             total = sum(p.numel() for p in params)
             self._flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
-        off = 0
-        for p in params:
-            self._flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-            off += p.numel()
+            self._views, off = [], 0
+            for p in params:
+                self._views.append(self._flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        torch._foreach_copy_(self._views, [p.grad for p in params])
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
         self._flat.div_(self.world)
-        off = 0
-        for p in params:
-            p.grad.copy_(self._flat[off:off + p.numel()].view_as(p.grad))
-            off += p.numel()
+        for p, v in zip(params, self._views):
+            p.grad = v
 
     def _step(self):
         b = self.batch

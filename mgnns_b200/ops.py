@@ -703,6 +703,18 @@ def _ln_backward(ctx, g):
 torch.library.register_autograd("mgnns::add_layernorm", _ln_backward, setup_context=_ln_setup)
 
 
+def rowmax(x2d: torch.Tensor):
+    """Row-wise max with first-index arg-max of a contiguous [rows, P] fp32 CUDA matrix (no autograd);
+    the kernel behind the 14x14 global max pool (ref: nn.MaxPool2d(14,14), model:302,:454,:486)."""
+    _need_cuda(x2d)
+    x2d = _f32c(x2d, "x")
+    rows, P = x2d.shape
+    pooled = torch.empty((rows,), device=x2d.device, dtype=torch.float32)
+    argmax = torch.empty((rows,), device=x2d.device, dtype=torch.int32)
+    _check(_lib.mgnns_rowmax_f32(x2d.data_ptr(), rows, P, pooled.data_ptr(), argmax.data_ptr(), _stream()), "rowmax")
+    return pooled, argmax
+
+
 # ----------------------------------------------------------------------------- image bank (+ global max pool)
 _LIB.define("imgbank(Tensor fmap, Tensor weight, Tensor bias) -> (Tensor, Tensor, Tensor)")
 

@@ -489,6 +489,32 @@ def test_linear_tc_fp32_mode_keeps_cuda_core_path_and_autograd(dev, ops):
     close(w.grad, wd.grad, 1e-4, 1e-3)
 
 
+@pytest.mark.parametrize("P", [196, 4, 128, 260, 512, 197, 7])
+def test_rowmax_ties_nan_inf_vs_torch(dev, ops, P):
+    """Global spatial max + first-index arg-max (ref: nn.MaxPool2d(14,14), model:302): vectorised kernel for
+    P % 4 == 0, scalar kernel otherwise; ties -> lowest index, NaN wins, all -inf rows -> index 0."""
+    rows = 1000
+    x = rnd(rows, P, seed=P)
+    x[1] = x[1].round()                       # many exact ties
+    x[2] = -3.5                               # constant row
+    x[3] = float('-inf')
+    x[4, P // 2] = float('nan')
+    x[5, P - 1] = float('nan')
+    x[5, 0] = float('nan')
+    x[6] = -x[6].abs() - 1.0                  # all negative
+    x[7, P - 1] = 100.0                       # max in the last slot
+    x[8] = 0.0
+    x[8, P // 3] = -0.0
+    pooled, argmax = ops.rowmax(x.to(dev))
+    ref_v, ref_i = x.max(dim=1)
+    nan_rows = torch.isnan(x).any(1)
+    assert torch.equal(torch.isnan(pooled.cpu()), nan_rows)
+    assert torch.equal(pooled.cpu()[~nan_rows], ref_v[~nan_rows])
+    first = (x == ref_v.unsqueeze(1)).float().argmax(1)                 # lowest index attaining the max
+    assert torch.equal(argmax.cpu().long()[~nan_rows], first[~nan_rows])
+    assert int(argmax[4]) == P // 2 and int(argmax[5]) == 0 and int(argmax[3]) == 0
+
+
 # ------------------------------------------------------------------------------------------- PMI
 KAT_VOCAB = ['PAD', 'UNK', 'a', 'b', 'c', 'd', 'e']
 KAT_DOCS = ["a b c a d", "b c d e", "a a b zzz c", "e d c b a b c"]
