@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--no-cfg2', action='store_true', help='skip the cfg-2 GraphConvolution microbench')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--no-branch-streams', action='store_true', help='run the independent channels / stacks on one stream')
     return ap.parse_args()
 
 
@@ -277,6 +278,7 @@ def ours(args):
 
     emap, count = synth.synthetic_edge_map(VOCAB, seed=0, docs=20000)
     model = build_model(dev, emap, count).train()
+    model.branch_streams = not args.no_branch_streams
     use_graph = not args.eager
     # same optimiser and hyper-parameters as the reference entry script (entry:164); fused=True only selects torch's
     # single-kernel implementation of the identical update
@@ -457,7 +459,7 @@ def ours(args):
                        "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (1.65 GB of feature maps per step; two alternating batches)",
                        "precision_mode": "%s for the image-bank contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
-                       "launch": launch_mode, "launch_note": graph_note,
+                       "launch": launch_mode, "launch_note": graph_note, "branch_streams": bool(model.branch_streams),
                        "kernel_timing": "per-kernel numbers from a separate eager pass of %d steps on the same inputs (CUDA events)" % KT},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(hbs[0]),

@@ -336,38 +336,94 @@ class Multi_GCN_Multihead_Att(nn.Module):
     # ------------------------------------------------------------------ forward (ref: model:431-567)
     def forward(self, text, text_lens, text_mask, object_feature, place_feature, object_inp, place_inp,
                 return_last_state=True):
-        text_feature = self.text_features(text)                                   # [B, 300]
-        text_memory_bank, _ = self.get_text_memory_bank(text, text_lens, True)    # [B, L, 300]
-
-        self.object_feature = self.object_features(object_feature)                # [B, 2048, 14, 14]
-        img_object_memory_bank, object_pooled = self._img_bank(self.object_feature, self.liner_img_object)
         query = self._query()
-        object_x_attention = self._label_channel(object_pooled, object_inp, 'object_A', self.object_attention,
-                                                 self.object_linear_5, self.object_x_linear, query)
-
-        self.place_feature = self.place_features(place_feature)
-        img_place_memory_bank, place_pooled = self._img_bank(self.place_feature, self.liner_img_place)
-        place_x_attention = self._label_channel(place_pooled, place_inp, 'place_A', self.place_attention,
-                                                self.place_linear_5, self.place_x_linear, query)
-
         text_mask = text_mask.to(torch.float32)
-        img_object_text = object_x_attention
-        for layer in self.img_object_text_multi_head_att:
-            img_object_text = layer(q=img_object_text, k=text_memory_bank, v=text_memory_bank, mask=text_mask)[0]
-        img_place_text = place_x_attention
-        for layer in self.img_place_text_multi_head_att:
-            img_place_text = layer(q=img_place_text, k=text_memory_bank, v=text_memory_bank, mask=text_mask)[0]
-        text_img_object = text_feature
-        for layer in self.text_img_object_multi_head_att:
-            text_img_object = layer(q=text_img_object, k=img_object_memory_bank, v=img_object_memory_bank)[0]
-        text_img_place = text_feature
-        for layer in self.text_img_place_multi_head_att:
-            text_img_place = layer(q=text_img_place, k=img_place_memory_bank, v=img_place_memory_bank)[0]
+
+        def text_gcn():
+            return self.text_features(text)                                           # [B, 300]
+
+        def text_bank():
+            return self.get_text_memory_bank(text, text_lens, True)[0]                # [B, L, 300]
+
+        def object_channel():
+            self.object_feature = self.object_features(object_feature)                # [B, 2048, 14, 14]
+            bank, pooled = self._img_bank(self.object_feature, self.liner_img_object)
+            return bank, self._label_channel(pooled, object_inp, 'object_A', self.object_attention,
+                                             self.object_linear_5, self.object_x_linear, query)
+
+        def place_channel():
+            self.place_feature = self.place_features(place_feature)
+            bank, pooled = self._img_bank(self.place_feature, self.liner_img_place)
+            return bank, self._label_channel(pooled, place_inp, 'place_A', self.place_attention,
+                                             self.place_linear_5, self.place_x_linear, query)
+
+        # the four channels are independent of each other (ref: model:444-506 runs them back to back)
+        text_feature, text_memory_bank, (img_object_memory_bank, object_x_attention), \
+            (img_place_memory_bank, place_x_attention) = self._run_branches(
+                [text_gcn, text_bank, object_channel, place_channel])
+
+        def stack(layers, q, bank, mask=None):
+            def run():
+                x = q
+                for layer in layers:
+                    x = layer(q=x, k=bank, v=bank, mask=mask)[0]
+                return x
+            return run
+
+        # ... and so are the four attention stacks (ref: model:509-546)
+        img_object_text, img_place_text, text_img_object, text_img_place = self._run_branches([
+            stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank, text_mask),
+            stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask),
+            stack(self.text_img_object_multi_head_att, text_feature, img_object_memory_bank),
+            stack(self.text_img_place_multi_head_att, text_feature, img_place_memory_bank)])
 
         multi_feature = torch.cat([text_img_object, text_img_place, img_object_text, img_place_text], dim=1)
         multi_feature = ops.linear(multi_feature, self.multi_linear_1.weight, self.multi_linear_1.bias)
         multi_feature = self.dropout(multi_feature)
         return ops.linear(multi_feature, self.multi_linear_2.weight, self.multi_linear_2.bias)
+
+    # ------------------------------------------------------------------ independent branches on side streams
+    def _run_branches(self, fns):
+        """Run independent sub-graphs of the forward.  With `branch_streams` (attribute, or env
+        MGNNS_BRANCH_STREAMS=1) they are forked onto side CUDA streams and joined afterwards, so their many
+        small latency-bound kernels overlap; autograd replays each backward op on its forward stream, so the
+        backward pass forks the same way, and a CUDA-graph capture records the branches as parallel paths.
+        Results are identical either way (same kernels, same order within a branch)."""
+        enabled = self.__dict__.get('branch_streams')
+        if enabled is None:
+            enabled = os.environ.get('MGNNS_BRANCH_STREAMS', '0') == '1'
+        dev = self.gc1.weight.device
+        if not enabled or dev.type != 'cuda' or len(fns) < 2:
+            return [fn() for fn in fns]
+        pool = self.__dict__.get('_branch_pool')
+        if pool is None or pool[0] != dev or len(pool[1]) < len(fns) - 1:
+            pool = (dev, [torch.cuda.Stream(device=dev) for _ in range(len(fns) - 1)])
+            self.__dict__['_branch_pool'] = pool
+        main = torch.cuda.current_stream(dev)
+        results = [None] * len(fns)
+        for i in range(1, len(fns)):
+            side = pool[1][i - 1]
+            side.wait_stream(main)                          # fork: after everything already enqueued on main
+            with torch.cuda.stream(side):
+                results[i] = fns[i]()
+        results[0] = fns[0]()
+        streams = [main] + pool[1][:len(fns) - 1]
+
+        def mark(obj, producer):
+            # outputs cross streams: tell the caching allocator about every stream that may read them
+            if torch.is_tensor(obj):
+                for s in streams:
+                    if s is not producer:
+                        obj.record_stream(s)
+            elif isinstance(obj, (tuple, list)):
+                for o in obj:
+                    mark(o, producer)
+
+        for i in range(1, len(fns)):
+            main.wait_stream(streams[i])                    # join
+        for i, r in enumerate(results):
+            mark(r, streams[i])
+        return results
 
     def get_config_optim(self, lr, lrp):
         """Optimiser groups exactly as the reference (model:569-585): the classifier tail, image-bank

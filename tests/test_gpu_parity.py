@@ -635,6 +635,32 @@ def test_full_model_logits_and_grads_vs_reference_golden(dev, golden):
         assert params[n].grad is None, n
 
 
+def test_branch_streams_match_single_stream(dev, golden):
+    """Forking the independent channels / attention stacks onto side CUDA streams (model.branch_streams) runs the
+    same kernels in the same per-branch order: logits and every gradient must match the single-stream run."""
+    zp = golden('pmi_synth300.npz')
+    cfg = dict(H.MODEL_CFG, B=16)
+    model = build_model(dev, cfg, H.edge_map_from_golden(zp, cfg['V']), int(zp['count'])).eval()
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    args = (text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    out = {}
+    for mode in (False, True):
+        model.branch_streams = mode
+        model.zero_grad(set_to_none=True)
+        for _ in range(3):                                   # repeat: allocator reuse across streams
+            model.zero_grad(set_to_none=True)
+            logits = model(*args)
+            torch.nn.functional.cross_entropy(logits, labels.to(dev)).backward()
+        torch.cuda.synchronize()
+        out[mode] = (logits.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()
+                                               if p.grad is not None})
+    assert torch.equal(out[False][0], out[True][0])
+    assert out[False][1].keys() == out[True][1].keys()
+    for n, g in out[False][1].items():
+        # weight gradients accumulated with fp32 atomics (image bank, text GCN) differ in summation order only
+        close(out[True][1][n], g, 1e-4, 1e-6, msg=n)
+
+
 def test_full_model_bigger_batch_vs_oracle_and_mvsa_labels(dev):
     """B=24 against the CPU oracle on a fresh seed, 7 and 3 labels (MVSA-shaped)."""
     for num_labels, seed in ((7, 23), (3, 24)):
