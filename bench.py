@@ -406,6 +406,8 @@ def ours(args):
     saved = (opt, reducer)
     opt, reducer = opt_e, red_e
     KT = 4
+    streams_on = model.branch_streams
+    model.branch_streams = False            # time each kernel alone on the current stream (no concurrent branches)
     step(dbs[0])
     torch.cuda.synchronize()
     ops.KernelTimers.reset(timer_names)
@@ -414,6 +416,7 @@ def ours(args):
     torch.cuda.synchronize()
     kt = {n: ops.KernelTimers.mean_ms(n) for n in timer_names}
     ops.KernelTimers.reset([])
+    model.branch_streams = streams_on
     opt, reducer = saved
     payload = red_e.payload_bytes() if red_e is not None else 0
 
@@ -460,7 +463,7 @@ def ours(args):
                        "l2": "inputs larger than L2 (1.65 GB of feature maps per step; two alternating batches)",
                        "precision_mode": "%s for the image-bank contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
                        "launch": launch_mode, "launch_note": graph_note, "branch_streams": bool(model.branch_streams),
-                       "kernel_timing": "per-kernel numbers from a separate eager pass of %d steps on the same inputs (CUDA events)" % KT},
+                       "kernel_timing": "per-kernel numbers from a separate eager, single-stream pass of %d steps on the same inputs (CUDA events around each launch)" % KT},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(hbs[0]),
                     "d2h_bytes_per_step": 4, "steps": E, "last_loss": loss_val,

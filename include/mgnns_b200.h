@@ -203,7 +203,9 @@ int mgnns_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, in
  * ref: self.liner_img_object / liner_img_place, models/Multi_GCN_Multihead_att.py:400-428
  * ------------------------------------------------------------------------- */
 int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias,
-                         int B, int C, int P, int O, int precision, float* bank, void* stream);
+                         int B, int C, int P, int O, int precision,
+                         float* workspace /* 2*O*C floats when precision == 1, else may be NULL */,
+                         float* bank, void* stream);
 int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O,
                         int precision, float* gW, void* stream);
 

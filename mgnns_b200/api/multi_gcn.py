@@ -399,6 +399,9 @@ class Multi_GCN_Multihead_Att(nn.Module):
         if pool is None or pool[0] != dev or len(pool[1]) < len(fns) - 1:
             pool = (dev, [torch.cuda.Stream(device=dev) for _ in range(len(fns) - 1)])
             self.__dict__['_branch_pool'] = pool
+            # gc1/gc2 are shared by the object and place channels: their AccumulateGrad nodes see gradients from
+            # two streams by design
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         main = torch.cuda.current_stream(dev)
         results = [None] * len(fns)
         for i in range(1, len(fns)):

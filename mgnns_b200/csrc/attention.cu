@@ -17,6 +17,68 @@ namespace mgnns {
 constexpr int AT_THREADS = 256;
 constexpr int AT_WARPS = AT_THREADS / 32;
 constexpr int HG = 4;  // heads processed together (register budget)
+constexpr int RING = 6; // ring slots per warp: two rows being consumed + four in flight (cp.async into a per-warp shared-memory ring)
+
+// Each warp streams its rows (warp, warp+8, ...) through a private ring of RING row slots filled with
+// 16-byte cp.async copies, so several rows (1.2 KB each at D=300) are in flight per warp without holding them in
+// registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Sum eight per-lane partials over the warp and leave all eight totals in every lane.  Three halving steps
+// (each lane sends the half of its values the partner keeps) bring it to one value per lane summed over eight
+// lanes, two more butterfly steps finish the sum, eight indexed shuffles broadcast: 17 shuffles, 9 adds.
+__device__ __forceinline__ void warp_reduce8(float (&v)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float a[4], c[2], d;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? v[i] : v[i + 4];
+        const float keep = b4 ? v[i + 4] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? a[i] : a[i + 2];
+        const float keep = b3 ? a[i + 2] : a[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = b2 ? c[0] : c[1];
+        const float keep = b2 ? c[1] : c[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    // value i = 4*b4 + 2*b3 + b2 lives in the lanes whose bits (4,3,2) spell i
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __shfl_sync(0xffffffffu, d, ((i >> 2) & 1) * 16 + ((i >> 1) & 1) * 8 + (i & 1) * 4);
+}
+
+template <int NV>
+__device__ __forceinline__ void ring_issue(float* slot, const float* row, int D4, int lane, bool live) {
+    if (live) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int c = lane + 32 * v;
+            if (c < D4) cp_async16(slot + 4 * c, row + 4 * c);
+        }
+    }
+    cp_async_commit();          // an empty group for a masked row keeps the group count uniform
+}
+template <int NV>
+__device__ __forceinline__ void ring_read(const float* slot, int D4, int lane, float4 (&k)[NV]) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c = lane + 32 * v;
+        k[v] = (c < D4) ? *reinterpret_cast<const float4*>(slot + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
@@ -28,7 +90,7 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
 __device__ __forceinline__ void scale4(float4& acc, float s) { acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s; }
 
 template <int NV>
-__global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask,
     int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
     float* __restrict__ ctx, float* __restrict__ attn, float* __restrict__ psum, float* __restrict__ lse) {
@@ -39,6 +101,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
     float* ws = wm + AT_WARPS * HG;          // [AT_WARPS][HG]
     float* fin = ws + AT_WARPS * HG;         // [HG] final max, [HG] final 1/sum, [AT_WARPS][HG] factors
     float* wacc = fin + 2 * HG + AT_WARPS * HG;  // [AT_WARPS][HG][D]  (16B aligned: all counts are multiples of 4)
+    float* ring = wacc + (size_t)AT_WARPS * HG * D;   // [AT_WARPS][RING][D]
+    float* kp = ring + (size_t)AT_WARPS * RING * D;    // [HG][L] dropout keep flags (1/0)
 
     const int b = blockIdx.x;
     const int h0 = blockIdx.y * HG;
@@ -64,63 +128,109 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
     const float* bk = bank + (int64_t)b * L * D;
     const float* mk = mask ? mask + (int64_t)b * L : nullptr;
 
-    auto load_row = [&](int l, float4 (&k)[NV]) {
-        const float* row = bk + (int64_t)l * D;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            int c = lane + 32 * v;
-            k[v] = (c < D4) ? ldg4(row + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* myring = ring + (size_t)warp * RING * D;
+    // live-row table in shared memory + the live bound Lb = 1 + last live row: padded text banks (mean 16 of
+    // 100 rows) stop there instead of walking the mask to L
+    unsigned char* lv = reinterpret_cast<unsigned char*>(kp + (size_t)HG * L);
+    __shared__ int s_lb;
+    if (threadIdx.x == 0) s_lb = 0;
+    for (int i = threadIdx.x; i < HG * L; i += AT_THREADS) sc[i] = -INFINITY;
+    __syncthreads();
+    {
+        int last = 0;
+        for (int l = threadIdx.x; l < L; l += AT_THREADS) {
+            const bool on = !(mk && mk[l] == 0.f);
+            lv[l] = on ? 1 : 0;
+            if (on) last = l + 1;
         }
-    };
-
-    float4 kcur[NV], knext[NV];
-    int l = warp;
-    bool cur_live = (l < L) && !(mk && mk[l] == 0.f);
-    if (cur_live) load_row(l, kcur);
-    while (l < L) {
-        const int ln = l + AT_WARPS;
-        const bool next_live = (ln < L) && !(mk && mk[ln] == 0.f);
-        if (next_live) load_row(ln, knext);
-        if (cur_live) {
-            float dot[HG];
-#pragma unroll
-            for (int h = 0; h < HG; ++h) {
-                float d = 0.f;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    int c = lane + 32 * v;
-                    if (c < D4) d += dot4(kcur[v], *reinterpret_cast<const float4*>(us + h * D + 4 * c));
-                }
-                dot[h] = warp_sum(d);
-            }
-#pragma unroll
-            for (int h = 0; h < HG; ++h) {
-                if (h < nh) {
-                    const float sv = dot[h] * scale;
-                    if (lane == 0) sc[h * L + l] = sv;
-                    bool keep = true;
-                    if (p_drop > 0.f) keep = uniform01(seed, ((uint64_t)b * H + h0 + h) * L + l) >= p_drop;
-                    const float mnew = fmaxf(m[h], sv);
-                    const float corr = __expf(m[h] - mnew);
-                    const float e = __expf(sv - mnew);
-                    s[h] = s[h] * corr + e;
-                    const float w = keep ? e : 0.f;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        scale4(acc[h][v], corr);
-                        fma4(acc[h][v], w, kcur[v]);
-                    }
-                    m[h] = mnew;
-                }
-            }
-        } else if (lane < nh) {
-            sc[lane * L + l] = -INFINITY;
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) kcur[v] = knext[v];
-        cur_live = next_live;
-        l = ln;
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (lane == 0 && last > 0) atomicMax(&s_lb, last);
     }
+    __syncthreads();
+    const int Lb = s_lb;
+    auto row_live = [&](int l) { return (l < Lb) && lv[l] != 0; };
+
+    // dropout keep flags for this sample's [nh, L] probabilities, computed once (the counter-based generator is
+    // ~25 integer instructions; per row and lane it used to be a quarter of the kernel's instruction stream)
+    if (p_drop > 0.f) {
+        for (int i = threadIdx.x; i < nh * L; i += AT_THREADS) {
+            const int h = i / L, l = i - h * L;
+            kp[i] = uniform01(seed, ((uint64_t)b * H + h0 + h) * L + l) >= p_drop ? 1.f : 0.f;
+        }
+        __syncthreads();
+    }
+
+    // Two rows per iteration: the query vectors are read from shared memory once per pair, and the eight dot
+    // products (2 rows x 4 heads) share one transposed butterfly reduction (17 shuffles instead of 40).
+    // prologue: the first two pairs in flight
+#pragma unroll
+    for (int j = 0; j < RING - 2; ++j) {
+        const int l = warp + j * AT_WARPS;
+        ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
+    }
+    int j0 = 0;                                          // ring index of the pair's first row
+    for (int l = warp; l < Lb; l += 2 * AT_WARPS, j0 += 2) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int lp = l + (RING - 2 + r) * AT_WARPS;
+            ring_issue<NV>(myring + ((j0 + RING - 2 + r) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+        }
+        cp_async_wait<RING - 2>();
+        __syncwarp();
+        const int lrow[2] = {l, l + AT_WARPS};
+        const bool live[2] = {row_live(lrow[0]), row_live(lrow[1])};
+        float4 k[2][NV];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (live[r]) ring_read<NV>(myring + ((j0 + r) % RING) * D, D4, lane, k[r]);
+            else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) k[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float dot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot[i] = 0.f;
+#pragma unroll
+        for (int h = 0; h < HG; ++h)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c = lane + 32 * v;
+                if (c < D4) {
+                    const float4 q = *reinterpret_cast<const float4*>(us + h * D + 4 * c);
+                    dot[h] += dot4(k[0][v], q);
+                    dot[HG + h] += dot4(k[1][v], q);
+                }
+            }
+        warp_reduce8(dot, lane);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (live[r]) {
+#pragma unroll
+                for (int h = 0; h < HG; ++h) {
+                    if (h < nh) {
+                        const float sv = dot[r * HG + h] * scale;
+                        if (lane == 0) sc[h * L + lrow[r]] = sv;
+                        if (sv > m[h]) {                 // warp-uniform: rescale only when the running max moves
+                            const float corr = __expf(m[h] - sv);
+                            s[h] *= corr;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) scale4(acc[h][v], corr);
+                            m[h] = sv;
+                        }
+                        const float e = __expf(sv - m[h]);
+                        s[h] += e;
+                        const float w = (p_drop > 0.f) ? e * kp[h * L + lrow[r]] : e;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) fma4(acc[h][v], w, k[r][v]);
+                    }
+                }
+            }                                        // masked rows keep the -inf the score table was initialised with
+        }
+        __syncwarp();                                // the slots are refilled by the next iteration's issue
+    }
+    cp_async_wait<0>();
+
 
     // ---- merge the per-warp partial softmax states --------------------------------
     if (lane == 0) {
@@ -165,8 +275,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
         float tot = 0.f;
         for (int ll = lane; ll < L; ll += 32) {
             float p = __expf(sc[h * L + ll] - M) * invS;
-            bool keep = true;
-            if (p_drop > 0.f) keep = uniform01(seed, ((uint64_t)b * H + h0 + h) * L + ll) >= p_drop;
+            const bool keep = (p_drop > 0.f) ? (kp[h * L + ll] != 0.f) : true;
             float pt = keep ? p * inv_keep : 0.f;
             attn[((int64_t)(h0 + h) * B + b) * L + ll] = pt;
             tot += pt;
@@ -177,7 +286,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_fwd_kernel(
 }
 
 template <int NV>
-__global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_bwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask,
     const float* __restrict__ lse, const float* __restrict__ gctx, const float* __restrict__ gpsum,
     int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
@@ -188,6 +297,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
     float* sc = gs + HG * D;             // [HG][L]  scores, then scale*ds
     float* tt = sc + HG * L;             // [HG][L]  <dctx,k>, then dropped-out probabilities
     float* wacc = tt + HG * L;           // [AT_WARPS][HG][D]; requires (2*HG*L) % 4 == 0 -> always
+    float* ring = wacc + (size_t)AT_WARPS * HG * D;   // [AT_WARPS][RING][D]
 
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -197,6 +307,24 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
     const float* mk = mask ? mask + (int64_t)b * L : nullptr;
     float* gb = gbank + (int64_t)b * L * D;
     if (seed_offset != nullptr) seed += *seed_offset;
+    float* myring = ring + (size_t)warp * RING * D;
+    unsigned char* lv = reinterpret_cast<unsigned char*>(ring + (size_t)AT_WARPS * RING * D);
+    __shared__ int s_lb;
+    if (threadIdx.x == 0) s_lb = 0;
+    __syncthreads();
+    {
+        int last = 0;
+        for (int l = threadIdx.x; l < L; l += AT_THREADS) {
+            const bool on = !(mk && mk[l] == 0.f);
+            lv[l] = on ? 1 : 0;
+            if (on) last = l + 1;
+        }
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (lane == 0 && last > 0) atomicMax(&s_lb, last);
+    }
+    __syncthreads();
+    const int Lb = s_lb;                 // 1 + last live row
+    auto row_live = [&](int l) { return (l < Lb) && lv[l] != 0; };
 
     for (int h0 = 0; h0 < H; h0 += HG) {
         const int nh = min(HG, H - h0);
@@ -205,37 +333,71 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
             us[i] = (i < nh * D) ? u[((int64_t)b * H + h0) * D + i] : 0.f;
             gs[i] = (i < nh * D) ? gctx[((int64_t)b * H + h0) * D + i] : 0.f;
         }
+        for (int i = threadIdx.x; i < HG * L; i += AT_THREADS) { sc[i] = -INFINITY; tt[i] = 0.f; }   // masked rows
         __syncthreads();
 
-        // ---- sweep A: s = <u,k>, t = <dctx,k> ---------------------------------------
-        for (int l = warp; l < L; l += AT_WARPS) {
-            const bool live = !(mk && mk[l] == 0.f);
-            if (!live) {
-                if (lane < HG) { sc[lane * L + l] = -INFINITY; tt[lane * L + l] = 0.f; }
-                continue;
-            }
-            float4 k[NV];
+        // ---- sweep A: s = <u,k>, t = <dctx,k>; two rows per iteration --------------------
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                int c = lane + 32 * v;
-                k[v] = (c < D4) ? ldg4(bk + (int64_t)l * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int j = 0; j < RING - 2; ++j) {
+            const int l = warp + j * AT_WARPS;
+            ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
+        }
+        int j0 = 0;
+        for (int l = warp; l < Lb; l += 2 * AT_WARPS, j0 += 2) {
 #pragma unroll
-            for (int h = 0; h < HG; ++h) {
-                float ds_ = 0.f, dt_ = 0.f;
+            for (int r = 0; r < 2; ++r) {
+                const int lp = l + (RING - 2 + r) * AT_WARPS;
+                ring_issue<NV>(myring + ((j0 + RING - 2 + r) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+            }
+            cp_async_wait<RING - 2>();
+            __syncwarp();
+            const int lrow[2] = {l, l + AT_WARPS};
+            const bool live[2] = {row_live(lrow[0]), row_live(lrow[1])};
+            float4 k[2][NV];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (live[r]) ring_read<NV>(myring + ((j0 + r) % RING) * D, D4, lane, k[r]);
+                else {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) k[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float ds_[8], dt_[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ds_[i] = 0.f; dt_[i] = 0.f; }
+#pragma unroll
+            for (int h = 0; h < HG; ++h)
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    int c = lane + 32 * v;
+                    const int c = lane + 32 * v;
                     if (c < D4) {
-                        ds_ += dot4(k[v], *reinterpret_cast<const float4*>(us + h * D + 4 * c));
-                        dt_ += dot4(k[v], *reinterpret_cast<const float4*>(gs + h * D + 4 * c));
+                        const float4 q = *reinterpret_cast<const float4*>(us + h * D + 4 * c);
+                        const float4 g = *reinterpret_cast<const float4*>(gs + h * D + 4 * c);
+                        ds_[h] += dot4(k[0][v], q);
+                        ds_[HG + h] += dot4(k[1][v], q);
+                        dt_[h] += dot4(k[0][v], g);
+                        dt_[HG + h] += dot4(k[1][v], g);
                     }
                 }
-                ds_ = warp_sum(ds_);
-                dt_ = warp_sum(dt_);
-                if (lane == 0) { sc[h * L + l] = ds_ * scale; tt[h * L + l] = dt_; }
+            warp_reduce8(ds_, lane);
+            warp_reduce8(dt_, lane);
+            if (lane < HG) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (live[r]) {
+                        // select this lane's head without dynamic register indexing
+                        float sv = ds_[r * HG], tv = dt_[r * HG];
+#pragma unroll
+                        for (int h = 1; h < HG; ++h)
+                            if (lane == h) { sv = ds_[r * HG + h]; tv = dt_[r * HG + h]; }
+                        sc[lane * L + lrow[r]] = sv * scale;
+                        tt[lane * L + lrow[r]] = tv;
+                    }
+                }
             }
+            __syncwarp();
         }
+        cp_async_wait<0>();
         __syncthreads();
 
         // ---- softmax backward on the [nh, L] table ----------------------------------
@@ -267,23 +429,32 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
         }
         __syncthreads();
 
-        // ---- sweep B: dbank rows and du ---------------------------------------------
+        // ---- sweep B: dbank rows and du (second read of the bank: mostly L2 hits).  One row per iteration: this
+        // sweep is FMA-bound (36 FMAs per head and float4), pairing rows only costs registers.
         float4 du[HG][NV];
 #pragma unroll
         for (int h = 0; h < HG; ++h)
 #pragma unroll
             for (int v = 0; v < NV; ++v) du[h][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int l = warp; l < L; l += AT_WARPS) {
-            const bool live = !(mk && mk[l] == 0.f);
+#pragma unroll
+        for (int j = 0; j < RING - 1; ++j) {
+            const int l = warp + j * AT_WARPS;
+            ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
+        }
+        j0 = 0;
+        for (int l = warp; l < L; l += AT_WARPS, ++j0) {
+            const int lp = l + (RING - 1) * AT_WARPS;
+            ring_issue<NV>(myring + ((j0 + RING - 1) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+            cp_async_wait<RING - 1>();
+            __syncwarp();
+            const bool live = row_live(l);
             float4 k[NV], dk[NV];
+            if (live) ring_read<NV>(myring + (j0 % RING) * D, D4, lane, k);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                int c = lane + 32 * v;
+                const int c = lane + 32 * v;
                 dk[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < D4) {
-                    if (h0 > 0) dk[v] = *reinterpret_cast<const float4*>(gb + (int64_t)l * D + 4 * c);
-                    if (live) k[v] = ldg4(bk + (int64_t)l * D + 4 * c);
-                }
+                if (c < D4 && h0 > 0) dk[v] = *reinterpret_cast<const float4*>(gb + (int64_t)l * D + 4 * c);
             }
             if (live) {
 #pragma unroll
@@ -291,7 +462,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
                     const float dsv = sc[h * L + l], pt = tt[h * L + l];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        int c = lane + 32 * v;
+                        const int c = lane + 32 * v;
                         if (c < D4) {
                             fma4(du[h][v], dsv, k[v]);
                             fma4(dk[v], pt, *reinterpret_cast<const float4*>(gs + h * D + 4 * c));
@@ -302,10 +473,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
             }
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                int c = lane + 32 * v;
+                const int c = lane + 32 * v;
                 if (c < D4) *reinterpret_cast<float4*>(gb + (int64_t)l * D + 4 * c) = dk[v];
             }
+            __syncwarp();
         }
+        cp_async_wait<0>();
 #pragma unroll
         for (int h = 0; h < HG; ++h)
 #pragma unroll
@@ -326,10 +499,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_q1_bwd_kernel(
 
 static size_t fwd_smem(int L, int D) {
     return sizeof(float) * ((size_t)HG * D + (size_t)HG * L + 2 * AT_WARPS * HG + 2 * HG + AT_WARPS * HG +
-                            (size_t)AT_WARPS * HG * D);
+                            (size_t)AT_WARPS * HG * D + (size_t)AT_WARPS * RING * D + (size_t)HG * L) + ((size_t)L + 15) / 16 * 16;
 }
 static size_t bwd_smem(int L, int D) {
-    return sizeof(float) * ((size_t)2 * HG * D + (size_t)2 * HG * L + (size_t)AT_WARPS * HG * D);
+    return sizeof(float) * ((size_t)2 * HG * D + (size_t)2 * HG * L + (size_t)AT_WARPS * HG * D + (size_t)AT_WARPS * RING * D) +
+           ((size_t)L + 15) / 16 * 16;
 }
 
 }  // namespace mgnns

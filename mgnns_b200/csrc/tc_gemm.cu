@@ -33,8 +33,8 @@ struct Params {
     int B, C, P, O;                      // samples, channels (2048), positions (196), outputs (300)
     const float* bias;                   // FWD
     float* out;                          // FWD: bank [B,P,O];  DW: gW [O,C]
-    int n_items;                         // FWD: B * m_tiles;   DW: c_tiles * groups
-    int m_tiles;                         // FWD: ceil(P/128)
+    int n_items;                         // FWD: ceil(B * bps / 4);   DW: c_tiles * groups
+    int bps;                             // FWD: 32-position boxes per sample, ceil(P/32)
     int groups, samples_per_group;       // DW
 };
 
@@ -64,7 +64,10 @@ struct Cfg {
 
 template <int PROBLEM, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, Params p) {
+    // FWD with SPLIT: W is split once per call in global memory (hi via tmB, lo via tmBlo); only A is split here.
+    constexpr bool B_PRESPLIT = SPLIT && PROBLEM == FWD;
     using G = Geo<PROBLEM>;
     using CF = Cfg<PROBLEM, SPLIT>;
     constexpr int STAGES = CF::STAGES;
@@ -124,18 +127,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kiters = item_kiters(item);
                 for (int kk = 0; kk < kiters; ++kk) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], G::A_BYTES + G::B_BYTES);
+                    mbar_expect_tx(&full[stage], G::A_BYTES + G::B_BYTES * (B_PRESPLIT ? 2 : 1));
                     uint8_t* a = stageA(stage);
                     uint8_t* b = stageB(stage);
                     if (PROBLEM == FWD) {
-                        const int smp = item / p.m_tiles, mt = item % p.m_tiles;
                         const int c0 = kk * KCHUNK;
-                        // A: four 32(p) x 32(c) boxes -> MN-major atoms 4 KB apart
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_3d(a + j * 4096, &tmA, &full[stage], mt * 128 + j * 32, c0, smp);
+                        // A: four 32(p) x 32(c) boxes -> MN-major atoms 4 KB apart.  The M tile is four consecutive
+                        // boxes of the (sample, 32-position box) sequence, so it may straddle two samples; boxes past
+                        // the last sample and positions >= P are zero-filled by TMA.
+                        for (int j = 0; j < 4; ++j) {
+                            const int g = item * 4 + j;
+                            const int smp = g / p.bps, pb = g - smp * p.bps;
+                            tma_load_3d(a + j * 4096, &tmA, &full[stage], pb * 32, c0, smp);
+                        }
                         // B: two 152-row boxes of W[o, c0:c0+32]
                         tma_load_2d(b, &tmB, &full[stage], c0, 0);
                         tma_load_2d(b + 152 * 128, &tmB, &full[stage], c0, 152);
+                        if (B_PRESPLIT) {
+                            uint8_t* bl = stageBlo(stage);
+                            tma_load_2d(bl, &tmBlo, &full[stage], c0, 0);
+                            tma_load_2d(bl + 152 * 128, &tmBlo, &full[stage], c0, 152);
+                        }
                     } else {
                         const int ct = item / p.groups, g = item % p.groups;
                         const int smp = g * p.samples_per_group + kk / p_chunks;
@@ -214,7 +226,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full[stage], phase);
                     float4* hi = reinterpret_cast<float4*>(stageA(stage));
                     float4* lo = reinterpret_cast<float4*>(stageAlo(stage));
-                    constexpr int NV = (G::A_BYTES + G::B_BYTES) / 16;     // A and B are contiguous, so are the lo buffers
+                    // A and B are contiguous, so are the lo buffers; a pre-split B needs no work here
+                    constexpr int NV = (G::A_BYTES + (B_PRESPLIT ? 0 : G::B_BYTES)) / 16;
 #pragma unroll 4
                     for (int i = t; i < NV; i += 128) {
                         float4 x = hi[i];
@@ -245,8 +258,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (kiters > 0) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
                 if (PROBLEM == FWD) {
-                    const int smp = item / p.m_tiles, mt = item % p.m_tiles;
-                    const int pp = mt * 128 + row;
+                    // this warp's 32 TMEM lanes are exactly one 32-position box
+                    const int g = item * 4 + q;
+                    const int smp = g / p.bps, pb = g - smp * p.bps;
+                    const int pp = (smp < p.B) ? pb * 32 + lane : p.P;
                     float* dst = p.out + ((int64_t)smp * p.P + pp) * p.O;
                     for (int c0 = 0; c0 < G::BN; c0 += 16) {
                         uint32_t r[16];
@@ -301,8 +316,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
+// W -> (hi, lo) with hi exactly representable in TF32 (done once per call for the forward's weight operand)
+__global__ void split_weight_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float x = w[i];
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
 template <int PROBLEM, bool SPLIT>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& blo, const Params& p, cudaStream_t st) {
     using CF = Cfg<PROBLEM, SPLIT>;
     static bool configured = false;
     if (!configured) {
@@ -314,7 +341,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, c
     }
     int grid = sm_count();
     if (grid > p.n_items) grid = p.n_items;
-    tc_gemm_kernel<PROBLEM, SPLIT><<<grid, NTHREADS, CF::SMEM_BYTES, st>>>(a, b, p);
+    tc_gemm_kernel<PROBLEM, SPLIT><<<grid, NTHREADS, CF::SMEM_BYTES, st>>>(a, b, blo, p);
     MG_LAUNCH_CHECK("tc_gemm");
     return 0;
 }
@@ -325,9 +352,10 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const Params& p, c
 using namespace mgnns;
 using namespace mgnns::tc;
 
-// bank[B,P,O] = fmap[B,C,P]^T . weight[O,C]^T + bias ; precision: 0 = tf32, 1 = 3xTF32 (fp32-class)
+// bank[B,P,O] = fmap[B,C,P]^T . weight[O,C]^T + bias ; precision: 0 = tf32, 1 = 3xTF32 (fp32-class; needs
+// 2*O*C floats of 16-byte aligned workspace for the split weight)
 extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias, int B, int C, int P, int O,
-                                    int precision, float* bank, void* stream) {
+                                    int precision, float* workspace, float* bank, void* stream) {
     MG_REQUIRE(B >= 0 && C >= 32 && P >= 1 && O >= 1, "imgbank_fwd_tc: bad dimensions");
     MG_REQUIRE(C % KCHUNK == 0, "imgbank_fwd_tc: C=%d must be a multiple of 32", C);
     MG_REQUIRE(O <= Geo<FWD>::BN && O % 4 == 0, "imgbank_fwd_tc: O=%d must be <= 304 and a multiple of 4", O);
@@ -335,7 +363,20 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
     if (B == 0) return 0;
     MG_REQUIRE(fmap && weight && bias && bank, "imgbank_fwd_tc: null pointer");
     MG_REQUIRE(aligned16(fmap) && aligned16(weight) && aligned16(bank), "imgbank_fwd_tc: operands must be 16-byte aligned");
-    CUtensorMap ma, mb;
+    cudaStream_t st = as_stream(stream);
+    const float* w_hi = weight;
+    const float* w_lo = weight;
+    if (precision) {
+        MG_REQUIRE(workspace && aligned16(workspace), "imgbank_fwd_tc: 3xTF32 needs 2*O*C floats of aligned workspace");
+        const int64_t n = (int64_t)O * C;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        split_weight_tf32_kernel<<<blocks, 256, 0, st>>>(weight, workspace, workspace + n, n);
+        MG_LAUNCH_CHECK("split_weight_tf32");
+        w_hi = workspace;
+        w_lo = workspace + n;
+    }
+    CUtensorMap ma, mb, mbl;
     {
         uint64_t dims[3] = {(uint64_t)P, (uint64_t)C, (uint64_t)B};
         uint64_t str[2] = {(uint64_t)P * 4, (uint64_t)C * P * 4};
@@ -346,16 +387,18 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
         uint64_t dims[2] = {(uint64_t)C, (uint64_t)O};
         uint64_t str[1] = {(uint64_t)C * 4};
         uint32_t box[2] = {32, 152};
-        if (int rc = make_map(&mb, weight, 2, dims, str, box)) return rc;
+        if (int rc = make_map(&mb, w_hi, 2, dims, str, box)) return rc;
+        if (int rc = make_map(&mbl, w_lo, 2, dims, str, box)) return rc;
     }
     Params p{};
     p.B = B; p.C = C; p.P = P; p.O = O;
     p.bias = bias; p.out = bank;
-    p.m_tiles = (P + 127) / 128;
-    p.n_items = B * p.m_tiles;
+    p.bps = (P + 31) / 32;
+    const int64_t items = ((int64_t)B * p.bps + 3) / 4;
+    MG_REQUIRE(items < (1LL << 29), "imgbank_fwd_tc: batch too large");
+    p.n_items = (int)items;
     p.groups = 1; p.samples_per_group = 1;
-    cudaStream_t st = as_stream(stream);
-    return precision ? launch<FWD, true>(ma, mb, p, st) : launch<FWD, false>(ma, mb, p, st);
+    return precision ? launch<FWD, true>(ma, mb, mbl, p, st) : launch<FWD, false>(ma, mb, mbl, p, st);
 }
 
 // gW[O,C] += sum_b gbank_b^T . fmap_b^T   (gW must be initialised by the caller)
@@ -389,8 +432,8 @@ extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B,
     if (groups > B) groups = B;
     p.groups = groups;
     p.samples_per_group = (B + groups - 1) / groups;
-    p.m_tiles = 1;
+    p.bps = 1;
     p.n_items = c_tiles * groups;
     cudaStream_t st = as_stream(stream);
-    return precision ? launch<DW, true>(ma, mb, p, st) : launch<DW, false>(ma, mb, p, st);
+    return precision ? launch<DW, true>(ma, mb, mb, p, st) : launch<DW, false>(ma, mb, mb, p, st);
 }

@@ -743,9 +743,11 @@ def _imgbank_impl(fmap, weight, bias):
         _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
     # bank_b [P,O] = fmap_b^T [P,C] @ weight^T [C,O] + bias
     if _tc_ok(C, P, O, 304):
+        prec = _PRECISIONS[_precision]
+        ws = torch.empty((2 * O * C,), device=fmap.device, dtype=torch.float32) if prec else None
         with _timed("imgbank_fwd"):
             _check(_lib.mgnns_imgbank_fwd_tc(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
-                                             _PRECISIONS[_precision], bank.data_ptr(), s), "imgbank_fwd_tc")
+                                             prec, _ptr(ws), bank.data_ptr(), s), "imgbank_fwd_tc")
         return bank, pooled, argmax
     for b0 in range(0, B, 65535):
         nb = min(65535, B - b0)
