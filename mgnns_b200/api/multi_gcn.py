@@ -357,76 +357,89 @@ class Multi_GCN_Multihead_Att(nn.Module):
             return bank, self._label_channel(pooled, place_inp, 'place_A', self.place_attention,
                                              self.place_linear_5, self.place_x_linear, query)
 
-        # the four channels are independent of each other (ref: model:444-506 runs them back to back)
-        text_feature, text_memory_bank, (img_object_memory_bank, object_x_attention), \
-            (img_place_memory_bank, place_x_attention) = self._run_branches(
-                [text_gcn, text_bank, object_channel, place_channel])
-
         def stack(layers, q, bank, mask=None):
-            def run():
-                x = q
-                for layer in layers:
-                    x = layer(q=x, k=bank, v=bank, mask=mask)[0]
-                return x
-            return run
+            x = q
+            for layer in layers:
+                x = layer(q=x, k=bank, v=bank, mask=mask)[0]
+            return x
 
-        # ... and so are the four attention stacks (ref: model:509-546)
-        img_object_text, img_place_text, text_img_object, text_img_place = self._run_branches([
-            stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank, text_mask),
-            stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask),
-            stack(self.text_img_object_multi_head_att, text_feature, img_object_memory_bank),
-            stack(self.text_img_place_multi_head_att, text_feature, img_place_memory_bank)])
+        streams = self._branch_streams(3)
+        if streams is None:
+            # one stream, the reference's order (ref: model:444-546)
+            text_feature = text_gcn()
+            text_memory_bank = text_bank()
+            img_object_memory_bank, object_x_attention = object_channel()
+            img_place_memory_bank, place_x_attention = place_channel()
+            img_object_text = stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank, text_mask)
+            img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask)
+            text_img_object = stack(self.text_img_object_multi_head_att, text_feature, img_object_memory_bank)
+            text_img_place = stack(self.text_img_place_multi_head_att, text_feature, img_place_memory_bank)
+        else:
+            # The forward is a small dependency graph: four independent channels, then four attention stacks that
+            # each need two of them.  Every chain stays on its own stream and waits only for the tensor it needs
+            # (events), so e.g. the image-query stacks overlap the LSTM.  Autograd replays each backward op on its
+            # forward stream, so the backward pass forks the same way; a CUDA-graph capture records parallel paths.
+            main, (s_txt, s_obj, s_plc) = streams
+            for side in (s_txt, s_obj, s_plc):
+                side.wait_stream(main)                      # fork: after everything already enqueued on main
+            with torch.cuda.stream(s_obj):
+                img_object_memory_bank, object_x_attention = object_channel()
+                ev_obj = s_obj.record_event()
+            with torch.cuda.stream(s_plc):
+                img_place_memory_bank, place_x_attention = place_channel()
+                ev_plc = s_plc.record_event()
+            with torch.cuda.stream(s_txt):
+                text_memory_bank = text_bank()
+                ev_bank = s_txt.record_event()
+            text_feature = text_gcn()
+            ev_tf = main.record_event()
+            with torch.cuda.stream(s_obj):
+                s_obj.wait_event(ev_tf)
+                text_img_object = stack(self.text_img_object_multi_head_att, text_feature, img_object_memory_bank)
+            with torch.cuda.stream(s_plc):
+                s_plc.wait_event(ev_tf)
+                text_img_place = stack(self.text_img_place_multi_head_att, text_feature, img_place_memory_bank)
+            with torch.cuda.stream(s_txt):
+                s_txt.wait_event(ev_obj)
+                img_object_text = stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank,
+                                        text_mask)
+            main.wait_event(ev_bank)
+            main.wait_event(ev_plc)
+            img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask)
+            for side in (s_txt, s_obj, s_plc):
+                main.wait_stream(side)                      # join
+            # tensors that crossed streams: tell the caching allocator about every stream that read them
+            for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt,)),
+                               (text_memory_bank, (main,)), (place_x_attention, (main,)),
+                               (text_img_object, (main,)), (text_img_place, (main,)), (img_object_text, (main,)),
+                               (text_mask, (s_txt,))):
+                for r in readers:
+                    t.record_stream(r)
 
         multi_feature = torch.cat([text_img_object, text_img_place, img_object_text, img_place_text], dim=1)
         multi_feature = ops.linear(multi_feature, self.multi_linear_1.weight, self.multi_linear_1.bias)
         multi_feature = self.dropout(multi_feature)
         return ops.linear(multi_feature, self.multi_linear_2.weight, self.multi_linear_2.bias)
 
-    # ------------------------------------------------------------------ independent branches on side streams
-    def _run_branches(self, fns):
-        """Run independent sub-graphs of the forward.  With `branch_streams` (attribute, or env
-        MGNNS_BRANCH_STREAMS=1) they are forked onto side CUDA streams and joined afterwards, so their many
-        small latency-bound kernels overlap; autograd replays each backward op on its forward stream, so the
-        backward pass forks the same way, and a CUDA-graph capture records the branches as parallel paths.
-        Results are identical either way (same kernels, same order within a branch)."""
+    # ------------------------------------------------------------------ side streams for the independent chains
+    def _branch_streams(self, n):
+        """(current stream, n side streams) when `branch_streams` is on (attribute, or env MGNNS_BRANCH_STREAMS=1)
+        and the model lives on a CUDA device; None otherwise.  Results are identical either way: same kernels, same
+        order within a chain."""
         enabled = self.__dict__.get('branch_streams')
         if enabled is None:
             enabled = os.environ.get('MGNNS_BRANCH_STREAMS', '0') == '1'
         dev = self.gc1.weight.device
-        if not enabled or dev.type != 'cuda' or len(fns) < 2:
-            return [fn() for fn in fns]
+        if not enabled or dev.type != 'cuda':
+            return None
         pool = self.__dict__.get('_branch_pool')
-        if pool is None or pool[0] != dev or len(pool[1]) < len(fns) - 1:
-            pool = (dev, [torch.cuda.Stream(device=dev) for _ in range(len(fns) - 1)])
+        if pool is None or pool[0] != dev or len(pool[1]) < n:
+            pool = (dev, [torch.cuda.Stream(device=dev) for _ in range(n)])
             self.__dict__['_branch_pool'] = pool
             # gc1/gc2 are shared by the object and place channels: their AccumulateGrad nodes see gradients from
             # two streams by design
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-        main = torch.cuda.current_stream(dev)
-        results = [None] * len(fns)
-        for i in range(1, len(fns)):
-            side = pool[1][i - 1]
-            side.wait_stream(main)                          # fork: after everything already enqueued on main
-            with torch.cuda.stream(side):
-                results[i] = fns[i]()
-        results[0] = fns[0]()
-        streams = [main] + pool[1][:len(fns) - 1]
-
-        def mark(obj, producer):
-            # outputs cross streams: tell the caching allocator about every stream that may read them
-            if torch.is_tensor(obj):
-                for s in streams:
-                    if s is not producer:
-                        obj.record_stream(s)
-            elif isinstance(obj, (tuple, list)):
-                for o in obj:
-                    mark(o, producer)
-
-        for i in range(1, len(fns)):
-            main.wait_stream(streams[i])                    # join
-        for i, r in enumerate(results):
-            mark(r, streams[i])
-        return results
+        return torch.cuda.current_stream(dev), tuple(pool[1][:n])
 
     def get_config_optim(self, lr, lrp):
         """Optimiser groups exactly as the reference (model:569-585): the classifier tail, image-bank
