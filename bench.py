@@ -490,6 +490,9 @@ def ours(args):
 
 def main():
     args = parse()
+    # a hung collective or capture must not hang the caller forever: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('MGNNS_BENCH_WATCHDOG_S', '900')), exit=True)
     # keep stdout clean for the ONE JSON line: libraries (NCCL banner, warnings) go to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)

@@ -30,7 +30,9 @@ class GraphedTrainStep:
         self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
         self.loss = None
         self.graph = None
+        self.graph_update = None
         self._flat = None
+        self._views = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -43,17 +45,29 @@ class GraphedTrainStep:
         ops.KernelTimers.enabled = set()
         try:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.loss = self._step()
-                self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+            if self.world == 1:
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._step()
+                    self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+            else:
+                # Two captured halves with the NCCL all-reduce issued eagerly between them: the collective is then
+                # an ordinary stream-ordered call of the process group (its own stream, watchdog and error
+                # handling untouched by capture), at the cost of one extra graph launch per step.
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._forward_backward()
+                    self._pack_grads()
+                    self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+                self.graph_update = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                    self._flat.div_(self.world)
+                    self._clip_and_step()
         finally:
             ops.set_seed_tensor(prev)
             ops.KernelTimers.enabled = timers
 
-    def _allreduce(self):
-        """One flat NCCL all-reduce of every gradient (SUM, then / world).  Gradients are packed with one
-        multi-tensor copy; afterwards each p.grad aliases its slice of the flat buffer (no copy back), which is
-        what clip_grad_norm_ and the optimizer then read."""
+    def _pack_grads(self):
+        """Gather every gradient into one flat buffer with a multi-tensor copy; afterwards each p.grad aliases
+        its slice (no copy back), which is what the all-reduce, clip_grad_norm_ and the optimizer then use."""
         params = [p for p in self.model.parameters() if p.grad is not None]
         if self._flat is None:
             total = sum(p.numel() for p in params)
@@ -63,22 +77,33 @@ class GraphedTrainStep:
                 self._views.append(self._flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
         torch._foreach_copy_(self._views, [p.grad for p in params])
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.div_(self.world)
         for p, v in zip(params, self._views):
             p.grad = v
 
-    def _step(self):
+    def _allreduce(self):
+        """The one collective of the step: flat NCCL all-reduce of the gradients (SUM; the / world follows)."""
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+
+    def _forward_backward(self):
         b = self.batch
         self.opt.zero_grad(set_to_none=True)
         logits = self.model(b['text'], self.lens_key, b['mask'], b['fo'], b['fp'], b['oinp'], b['pinp'])
         loss = self.crit(logits, b['labels'])
         loss.backward()
-        if self.world > 1:
-            self._allreduce()
+        return loss.detach()
+
+    def _clip_and_step(self):
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
         self.opt.step()
-        return loss.detach()
+
+    def _step(self):
+        loss = self._forward_backward()
+        if self.world > 1:
+            self._pack_grads()
+            self._allreduce()
+            self._flat.div_(self.world)
+        self._clip_and_step()
+        return loss
 
     def update_lengths(self, lens_cpu):
         """New batch in the static buffers: refresh the LSTM schedule (tiny H2D on the current stream)."""
@@ -86,4 +111,7 @@ class GraphedTrainStep:
 
     def replay(self):
         self.graph.replay()
+        if self.world > 1:
+            self._allreduce()
+            self.graph_update.replay()
         return self.loss
