@@ -246,6 +246,52 @@ def gcn_cfg2_microbench(dev, peaks):
             "dense_gflop": dense_flop / 1e9, "sparse_gflop": 2.0 * B * nnz * Fin / 1e9}
 
 
+def pmi_microbench(dev, peaks, docs=200000, cpu_docs=4000):
+    """§8 row a1 (ref: utils/pmi.py:40-58): windowed co-occurrence counts of a synthetic TumEmo-shaped corpus
+    (200k docs x 100 padded tokens, V=20,154, window 6, min co-occurrence 2) on the GPU — dense int32 count table
+    + ordered CSR compaction — beside the oracle's vectorised numpy port on a bounded sample."""
+    import numpy as np
+    import torch
+    from mgnns_b200 import ops, synth
+    from oracle import pmi_oracle as PO
+    text, lens, _ = synth.make_texts(docs, VOCAB, CFG['L'], seed=7)
+    tok = text.to(torch.int32).to(dev)
+    for _ in range(2):
+        out = ops.pmi_count(tok, VOCAB, 6, 0, 2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 3
+    for _ in range(iters):
+        rowptr, col, cnt, wc = ops.pmi_count(tok, VOCAB, 6, 0, 2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    live = int(lens.clamp(max=CFG['L']).sum())
+    ids = text[:cpu_docs].numpy()
+    t0 = time.perf_counter()
+    pair, wc_cpu = PO.counts_numpy(ids, 0, VOCAB, 6)
+    cpu_s = time.perf_counter() - t0
+    # bit-exactness of the sample (checker only): GPU counts of the same documents
+    r2, c2, n2, w2 = ops.pmi_count(tok[:cpu_docs].contiguous(), VOCAB, 6, 0, 1)
+    rows = np.repeat(np.arange(VOCAB), np.diff(r2.cpu().numpy().astype(np.int64)))
+    dense = np.zeros_like(pair)
+    dense[rows, c2.cpu().numpy().astype(np.int64)] = n2.cpu().numpy()
+    exact = bool(np.array_equal(dense, pair) and np.array_equal(w2.cpu().numpy(), wc_cpu))
+    del pair, dense
+    table_bytes = 4.0 * VOCAB * VOCAB
+    return {"workload": "PMI co-occurrence counts: %d docs x 100 tokens (%d non-pad), V=%d, window 6, min_cooccurence 2"
+                        % (docs, live, VOCAB),
+            "gpu_ms": ms, "docs_per_s": docs / ms * 1e3, "kept_cells": int(col.numel()),
+            "hbm_bytes": 3 * table_bytes + 4.0 * docs * CFG['L'],
+            "hbm_gbs": (3 * table_bytes + 4.0 * docs * CFG['L']) / ms / 1e6,
+            "frac_of_measured_hbm": (3 * table_bytes + 4.0 * docs * CFG['L']) / ms / 1e6 / peaks['hbm_gbs'],
+            "bytes_note": "dense int32 [V,V] table zeroed, scanned for row counts and scanned again for the ordered CSR fill",
+            "cpu_port": {"docs": cpu_docs, "seconds": cpu_s, "docs_per_s": cpu_docs / cpu_s, "cores": 1,
+                         "kind": "port (oracle/pmi_oracle.counts_numpy)"},
+            "sample_bit_exact": exact}
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -397,7 +443,8 @@ def ours(args):
     t = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * E / t.item()
+    e2e_seconds = t.item()
+    e2e_value = world * B * E / e2e_seconds
 
     # ---- per-kernel timing pass (eager, same inputs): CUDA events around the hand-written kernels -------
     timer_names = ['imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd', 'lstm_rec_fwd', 'lstm_rec_bwd']
@@ -434,20 +481,28 @@ def ours(args):
     byts = {'imgbank_fwd': 4.0 * (B * C * P_ + B * P_ * O_ + O_ * C), 'imgbank_dw': 4.0 * (B * C * P_ + B * P_ * O_ + O_ * C),
             'rowmax': 4.0 * (B * C * P_ + 2 * B * C),
             'attn_q1_fwd': 4.0 * B * (P_ + 100) / 2 * 300, 'attn_q1_bwd': 4.0 * B * (P_ + 100) * 300}
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom, {}).get('dram_bytes_per_launch')
     if dom in flop:
         # fp32 CUDA-core GEMM today: the bound a tensor-core version will be held to is the TF32 pipe
         # (half the measured dense bf16 rate)
         peak = peaks['bf16_tflops_sustained'] / 2.0
         ach = flop[dom] / (dom_ms * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
+                "frac": ach / peak, "traffic": traffic, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
                 "share_of_step": dom_ms * dom_cnt / KT / ms_step,
                 "peak_source": peaks['source'] + "; TF32 = bf16_tflops_sustained/2",
+                "mma_work_factor": 3.0 * (224.0 / 196.0) * (304.0 / 300.0) if ops.get_precision() == 'tf32x3' else (224.0 / 196.0) * (304.0 / 300.0),
+                "mma_note": "3xTF32 issues 3 MMAs per algorithmic product, tiles pad 196->224 positions and 300->304 outputs: "
+                            "tensor-pipe utilisation = frac x mma_work_factor",
                 "algorithmic_flop_per_launch": flop[dom], "algorithmic_bytes_per_launch": byts[dom]}
     else:
         ach = byts[dom] / (dom_ms * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks['hbm_gbs'], "unit": "GB/s",
-                "frac": ach / peaks['hbm_gbs'], "traffic": None, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
+                "frac": ach / peaks['hbm_gbs'], "traffic": traffic, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
                 "share_of_step": dom_ms * dom_cnt / KT / ms_step, "peak_source": peaks['source'],
                 "algorithmic_bytes_per_launch": byts[dom]}
     kernels = {n: {"ms_per_launch": ms, "launches_per_step": cnt / KT,
@@ -468,7 +523,10 @@ def ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(hbs[0]),
                     "d2h_bytes_per_step": 4, "steps": E, "last_loss": loss_val,
                     "how": "pinned host batch -> H2D on a copy stream (prefetch depth 1) -> model/backward/"
-                           "clip/Adam through the nn.Module API -> loss.item()"},
+                           "clip/Adam through the nn.Module API -> loss.item()",
+                    "h2d_gbs_per_gpu": h2d_bytes(hbs[0]) * E / e2e_seconds / 1e9,
+                    "bound": "host->device copy of the fp32 feature maps (1.6 GB per 512-sample step per GPU); "
+                             "the device-resident step is shorter than the copy"},
             "gpu_launches": int(launches),
             "roofline": roof, "kernels": kernels}
     if world > 1:
@@ -482,6 +540,11 @@ def ours(args):
                 line["gcn_layer_cfg2"] = gcn_cfg2_microbench(dev, peaks)
             except Exception as exc:       # keep the headline line even if the microbench cannot allocate
                 line["gcn_layer_cfg2"] = {"error": str(exc)[:200]}
+        if not args.no_cfg2:
+            try:
+                line["pmi_count"] = pmi_microbench(dev, peaks)
+            except Exception as exc:
+                line["pmi_count"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline:
             r = cpu_reference_run(3, 1, args.cpu_batch)
             line["cpu_baseline"] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -13,6 +13,31 @@ namespace mgnns {
 
 constexpr int SPMM_EDGE_CHUNK = 256;
 
+// L2 residency hints: the gathered rows of X_b are re-read ~nnz/N times from L2 while the output rows stream
+// through it once, so X is loaded with an evict_last policy and Y is stored with evict_first.  Measured at
+// batch 64: DRAM reads 2.13 -> 1.99 GB for 0.77 GB of X (the remainder is each L2 die fetching its own copy of
+// X_b); the kernel is bound by L2->SM gather bandwidth either way.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg4_l2(const float* ptr, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void stg4_l2(float* ptr, const float4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(128) spmm_csr_kernel(
     int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -24,6 +49,7 @@ __global__ void __launch_bounds__(128) spmm_csr_kernel(
     const float* Xb = X + (int64_t)b * strideX;
     float* Yb = Y + (int64_t)b * strideY;
     const int nvec = VEC ? (F >> 2) : F;
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
     const int row0 = blockIdx.x * rows_per_cta;
     for (int r = row0; r < row0 + rows_per_cta && r < n_rows; ++r) {
         const int e0 = rowptr[r], e1 = rowptr[r + 1];
@@ -42,10 +68,10 @@ __global__ void __launch_bounds__(128) spmm_csr_kernel(
                     int e = 0;
                     if (VEC) {
                         for (; e + 4 <= cn; e += 4) {
-                            float4 x0 = ldg4(Xb + (int64_t)s_col[e + 0] * ldx + 4 * f);
-                            float4 x1 = ldg4(Xb + (int64_t)s_col[e + 1] * ldx + 4 * f);
-                            float4 x2 = ldg4(Xb + (int64_t)s_col[e + 2] * ldx + 4 * f);
-                            float4 x3 = ldg4(Xb + (int64_t)s_col[e + 3] * ldx + 4 * f);
+                            float4 x0 = ldg4_l2(Xb + (int64_t)s_col[e + 0] * ldx + 4 * f, keep);
+                            float4 x1 = ldg4_l2(Xb + (int64_t)s_col[e + 1] * ldx + 4 * f, keep);
+                            float4 x2 = ldg4_l2(Xb + (int64_t)s_col[e + 2] * ldx + 4 * f, keep);
+                            float4 x3 = ldg4_l2(Xb + (int64_t)s_col[e + 3] * ldx + 4 * f, keep);
                             float v0 = s_val[e], v1 = s_val[e + 1], v2 = s_val[e + 2], v3 = s_val[e + 3];
                             acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y);
                             acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
@@ -57,7 +83,7 @@ __global__ void __launch_bounds__(128) spmm_csr_kernel(
                             acc.z = fmaf(v3, x3.z, acc.z); acc.w = fmaf(v3, x3.w, acc.w);
                         }
                         for (; e < cn; ++e) {
-                            float4 x0 = ldg4(Xb + (int64_t)s_col[e] * ldx + 4 * f);
+                            float4 x0 = ldg4_l2(Xb + (int64_t)s_col[e] * ldx + 4 * f, keep);
                             float v0 = s_val[e];
                             acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y);
                             acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
@@ -69,7 +95,7 @@ __global__ void __launch_bounds__(128) spmm_csr_kernel(
                 }
             }
             if (f < nvec) {
-                if (VEC) *reinterpret_cast<float4*>(Yb + (int64_t)r * ldy + 4 * f) = acc;
+                if (VEC) stg4_l2(Yb + (int64_t)r * ldy + 4 * f, acc, stream);
                 else Yb[(int64_t)r * ldy + f] = acc.x;
             }
         }

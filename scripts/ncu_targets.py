@@ -28,24 +28,17 @@ if which in ('attn', 'all'):
             ctx, attn, psum, lse = torch.ops.mgnns.attn_q1(u, bank, mask, 0.088, 0.0, 0)
             ctx.sum().backward()
     torch.cuda.synchronize()
-if which in ('spmm', 'all'):
-    import numpy as np
+if which in ('spmm', 'gcn', 'all'):
+    from mgnns_b200 import synth
     from mgnns_b200.api.graph_util import CSRAdjacency
+    from mgnns_b200.api.multi_gcn import GraphConvolution
     N, F, Bs = 10000, 300, int(os.environ.get('BS', 32))
-    rs = np.random.RandomState(0)
-    deg = np.clip((rs.pareto(1.3, N) + 1) * 20, 1, 3000).astype(np.int64)
-    deg = np.maximum(1, (deg * (64.0 * N / deg.sum())).astype(np.int64))
-    pop = (rs.pareto(1.1, N) + 1); pop /= pop.sum()
-    rows, cols = [], []
-    for i in range(N):
-        c = np.unique(np.concatenate([rs.choice(N, deg[i], p=pop), [i]]))
-        rows.append(np.full(c.shape, i)); cols.append(c)
-    rows, cols = np.concatenate(rows), np.concatenate(cols)
-    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=N))])
-    val = (1.0 / np.diff(rowptr))[rows].astype(np.float32)
+    rowptr, cols, val = synth.cfg2_word_graph(N, seed=0)
     csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, dev)
+    gc = GraphConvolution(F, 512).to(dev)
     x = torch.randn(Bs, N, F, device=dev)
-    for _ in range(3):
-        y = csr.spmm(x)
+    with torch.no_grad():
+        for _ in range(3):
+            y = gc(x, csr, ops.ACT_RELU) if which != 'spmm' else csr.spmm(x)
     torch.cuda.synchronize()
 print('done', which)
