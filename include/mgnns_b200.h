@@ -205,6 +205,8 @@ int mgnns_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, in
 int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias,
                          int B, int C, int P, int O, int precision,
                          float* workspace /* 2*O*C floats when precision == 1, else may be NULL */,
+                         float* pooled /* optional [B,C]: global spatial max (ref: nn.MaxPool2d(14,14), model:302) fused
+                                          into the operand pass; precision == 1 only, else NULL */,
                          float* bank, void* stream);
 int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O,
                         int precision, float* gW, void* stream);

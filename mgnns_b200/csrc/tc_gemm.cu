@@ -24,6 +24,13 @@
 namespace mgnns {
 namespace tc {
 
+// order-preserving float -> uint key (larger float <=> larger key); any NaN maps to the top key
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    const uint32_t k = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+    return ((u << 1) > 0xFF000000u) ? 0xFFC00000u : k;
+}
+
 constexpr int KCHUNK = 32;               // fp32 elements per 128-byte swizzle row
 constexpr int UMMA_K = 8;                // tf32
 constexpr int NTHREADS = 384;
@@ -35,6 +42,7 @@ struct Params {
     float* out;                          // FWD: bank [B,P,O];  DW: gW [O,C]
     int n_items;                         // FWD: ceil(B * bps / 4);   DW: c_tiles * groups
     int bps;                             // FWD: 32-position boxes per sample, ceil(P/32)
+    uint32_t* pooled_ord;                // FWD + SPLIT: [B,C] running spatial max as order-preserving uints (or NULL)
     int groups, samples_per_group;       // DW
 };
 
@@ -220,29 +228,98 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int t = threadIdx.x - 128;
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t pool_o[8];
+            int pool_smp[4], pool_lim[4], pool_c0 = 0;
+            bool pool_pending = false;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int kiters = item_kiters(item);
+                if (PROBLEM == FWD && p.pooled_ord != nullptr) {
+#pragma unroll
+                    for (int box = 0; box < 4; ++box) {
+                        const int g = item * 4 + box;
+                        const int smp = g / p.bps, pb = g - smp * p.bps;
+                        pool_smp[box] = smp;
+                        pool_lim[box] = (smp < p.B) ? min(32, p.P - pb * 32) : 0;     // valid positions of the box
+                    }
+                }
                 for (int kk = 0; kk < kiters; ++kk) {
                     mbar_wait(&full[stage], phase);
                     float4* hi = reinterpret_cast<float4*>(stageA(stage));
                     float4* lo = reinterpret_cast<float4*>(stageAlo(stage));
-                    // A and B are contiguous, so are the lo buffers; a pre-split B needs no work here
-                    constexpr int NV = (G::A_BYTES + (B_PRESPLIT ? 0 : G::B_BYTES)) / 16;
+                    if (PROBLEM == FWD && p.pooled_ord != nullptr) {
+                        // Fused 14x14 global max pool (ref: nn.MaxPool2d(14,14), model:302,:454,:486): this pass touches
+                        // every element of the feature map anyway.  Float4 `idx` of the A region is box idx/256 (32
+                        // positions), channel row (idx%256)/8, physical 16-byte chunk idx%8; SWIZZLE_128B with 32-byte
+                        // atoms stores logical atom a of row r at physical atom a ^ (r & 3).  Each thread keeps one
+                        // order-preserving uint per float4 (NaN maps above +inf, like torch's max pooling); the
+                        // shuffles and atomics that finish the reduction run AFTER the stage has been handed to the
+                        // MMA issuer, off the critical path.
+                        const int qphys = t & 7;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = t + i * 128;
+                            const float4 x = hi[idx];
+                            float4 h, l;
+                            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                            hi[idx] = h;
+                            lo[idx] = l;
+                            const int r = (t >> 3) + 16 * (i & 1);
+                            const int qlog = (((qphys >> 1) ^ (r & 3)) << 1) | (qphys & 1);
+                            pool_o[i] = (4 * qlog < pool_lim[i >> 1])
+                                            ? max(max(ordered_key(x.x), ordered_key(x.y)), max(ordered_key(x.z), ordered_key(x.w)))
+                                            : 0u;
+                        }
+                        pool_pending = true;
+                        pool_c0 = kk * KCHUNK;
+                    } else {
+                        // A and B are contiguous, so are the lo buffers; a pre-split B needs no work here
+                        constexpr int NV = (G::A_BYTES + (B_PRESPLIT ? 0 : G::B_BYTES)) / 16;
 #pragma unroll 4
-                    for (int i = t; i < NV; i += 128) {
-                        float4 x = hi[i];
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-                        hi[i] = h;
-                        lo[i] = l;
+                        for (int i = t; i < NV; i += 128) {
+                            float4 x = hi[i];
+                            float4 h, l;
+                            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                            hi[i] = h;
+                            lo[i] = l;
+                        }
                     }
                     fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ready[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (PROBLEM == FWD && pool_pending) {
+                        // boxes of the same sample are merged in registers first (a tile spans at most a few samples);
+                        // then the eight lanes of a channel row reduce and one lane issues a fire-and-forget atomicMax
+#pragma unroll
+                        for (int rp = 0; rp < 2; ++rp) {
+                            const int r = (t >> 3) + 16 * rp;
+                            uint32_t acc = 0;
+                            int acc_smp = pool_smp[0];
+#pragma unroll
+                            for (int box = 0; box < 4; ++box) {
+                                if (pool_smp[box] != acc_smp) {                     // warp-uniform
+                                    acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+                                    acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+                                    acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+                                    if ((t & 7) == 0 && acc != 0) atomicMax(p.pooled_ord + (int64_t)acc_smp * p.C + pool_c0 + r, acc);
+                                    acc = 0;
+                                    acc_smp = pool_smp[box];
+                                }
+                                acc = max(acc, pool_o[box * 2 + rp]);
+                            }
+                            acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+                            acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+                            acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+                            if ((t & 7) == 0 && acc != 0) atomicMax(p.pooled_ord + (int64_t)acc_smp * p.C + pool_c0 + r, acc);
+                        }
+                        pool_pending = false;
+                    }
                 }
             }
         }
@@ -316,6 +393,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
+// order-preserving uint -> float, in place (the fused max pool accumulates with integer atomicMax)
+__global__ void ordered_to_float_kernel(uint32_t* __restrict__ v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t o = v[i];
+        v[i] = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    }
+}
+
 // W -> (hi, lo) with hi exactly representable in TF32 (done once per call for the forward's weight operand)
 __global__ void split_weight_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,9 +439,10 @@ using namespace mgnns;
 using namespace mgnns::tc;
 
 // bank[B,P,O] = fmap[B,C,P]^T . weight[O,C]^T + bias ; precision: 0 = tf32, 1 = 3xTF32 (fp32-class; needs
-// 2*O*C floats of 16-byte aligned workspace for the split weight)
+// 2*O*C floats of 16-byte aligned workspace for the split weight).  pooled (optional, [B,C], 3xTF32 only):
+// global spatial max of the feature map, fused into the operand pass.
 extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias, int B, int C, int P, int O,
-                                    int precision, float* workspace, float* bank, void* stream) {
+                                    int precision, float* workspace, float* pooled, float* bank, void* stream) {
     MG_REQUIRE(B >= 0 && C >= 32 && P >= 1 && O >= 1, "imgbank_fwd_tc: bad dimensions");
     MG_REQUIRE(C % KCHUNK == 0, "imgbank_fwd_tc: C=%d must be a multiple of 32", C);
     MG_REQUIRE(O <= Geo<FWD>::BN && O % 4 == 0, "imgbank_fwd_tc: O=%d must be <= 304 and a multiple of 4", O);
@@ -363,7 +450,12 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
     if (B == 0) return 0;
     MG_REQUIRE(fmap && weight && bias && bank, "imgbank_fwd_tc: null pointer");
     MG_REQUIRE(aligned16(fmap) && aligned16(weight) && aligned16(bank), "imgbank_fwd_tc: operands must be 16-byte aligned");
+    MG_REQUIRE(pooled == nullptr || precision == 1, "imgbank_fwd_tc: the fused max pool needs the 3xTF32 mode (operand splitter pass)");
     cudaStream_t st = as_stream(stream);
+    if (pooled) {
+        cudaError_t e = cudaMemsetAsync(pooled, 0, (size_t)B * C * sizeof(float), st);
+        MG_REQUIRE(e == cudaSuccess, "imgbank_fwd_tc: memset failed: %s", cudaGetErrorString(e));
+    }
     const float* w_hi = weight;
     const float* w_lo = weight;
     if (precision) {
@@ -398,7 +490,14 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
     MG_REQUIRE(items < (1LL << 29), "imgbank_fwd_tc: batch too large");
     p.n_items = (int)items;
     p.groups = 1; p.samples_per_group = 1;
-    return precision ? launch<FWD, true>(ma, mb, mbl, p, st) : launch<FWD, false>(ma, mb, mbl, p, st);
+    p.pooled_ord = reinterpret_cast<uint32_t*>(pooled);
+    if (int rc = precision ? launch<FWD, true>(ma, mb, mbl, p, st) : launch<FWD, false>(ma, mb, mbl, p, st)) return rc;
+    if (pooled) {
+        const int64_t n = (int64_t)B * C;
+        ordered_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.pooled_ord, n);
+        MG_LAUNCH_CHECK("ordered_to_float");
+    }
+    return 0;
 }
 
 // gW[O,C] += sum_b gbank_b^T . fmap_b^T   (gW must be initialised by the caller)
@@ -433,6 +532,7 @@ extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B,
     p.groups = groups;
     p.samples_per_group = (B + groups - 1) / groups;
     p.bps = 1;
+    p.pooled_ord = nullptr;
     p.n_items = c_tiles * groups;
     cudaStream_t st = as_stream(stream);
     return precision ? launch<DW, true>(ma, mb, mb, p, st) : launch<DW, false>(ma, mb, mb, p, st);

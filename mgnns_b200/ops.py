@@ -737,17 +737,25 @@ def _imgbank_impl(fmap, weight, bias):
     O = weight.shape[0]
     bank = torch.empty((B, P, O), device=fmap.device, dtype=torch.float32)
     pooled = torch.empty((B, C), device=fmap.device, dtype=torch.float32)
-    argmax = torch.empty((B, C), device=fmap.device, dtype=torch.int32)
     s = _stream()
+    prec = _PRECISIONS[_precision]
+    if _tc_ok(C, P, O, 304) and prec == 1:
+        # 3xTF32: the operand-splitter pass of the tensor-core kernel also produces the 14x14 global max, so the
+        # feature map is read from HBM once; the arg-max is only needed by the feature-map gradient and is
+        # recomputed there (empty placeholder here)
+        ws = torch.empty((2 * O * C,), device=fmap.device, dtype=torch.float32)
+        with _timed("imgbank_fwd"):
+            _check(_lib.mgnns_imgbank_fwd_tc(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
+                                             prec, ws.data_ptr(), pooled.data_ptr(), bank.data_ptr(), s), "imgbank_fwd_tc")
+        return bank, pooled, torch.empty((0,), device=fmap.device, dtype=torch.int32)
+    argmax = torch.empty((B, C), device=fmap.device, dtype=torch.int32)
     with _timed("rowmax"):
         _check(_lib.mgnns_rowmax_f32(fmap.data_ptr(), B * C, P, pooled.data_ptr(), argmax.data_ptr(), s), "rowmax")
     # bank_b [P,O] = fmap_b^T [P,C] @ weight^T [C,O] + bias
     if _tc_ok(C, P, O, 304):
-        prec = _PRECISIONS[_precision]
-        ws = torch.empty((2 * O * C,), device=fmap.device, dtype=torch.float32) if prec else None
         with _timed("imgbank_fwd"):
             _check(_lib.mgnns_imgbank_fwd_tc(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
-                                             prec, _ptr(ws), bank.data_ptr(), s), "imgbank_fwd_tc")
+                                             prec, None, None, bank.data_ptr(), s), "imgbank_fwd_tc")
         return bank, pooled, argmax
     for b0 in range(0, B, 65535):
         nb = min(65535, B - b0)
@@ -760,8 +768,9 @@ def _imgbank_impl(fmap, weight, bias):
 def _imgbank_fake(fmap, weight, bias):
     B, C = fmap.shape[0], fmap.shape[1]
     P = fmap.numel() // (B * C)
+    fused = _PRECISIONS[_precision] == 1 and _tc_ok(C, P, weight.shape[0], 304)
     return (fmap.new_empty((B, P, weight.shape[0])), fmap.new_empty((B, C)),
-            fmap.new_empty((B, C), dtype=torch.int32))
+            fmap.new_empty((0,) if fused else (B, C), dtype=torch.int32))
 
 
 _LIB.impl("imgbank", _imgbank_impl, "CUDA")
@@ -812,6 +821,13 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
                          batch=nb)
         if g_pooled is not None:
             g_pooled = _f32c(g_pooled, "grad_pooled")
+            if argmax.numel() == 0:
+                # fused forward: recompute the first-index arg-max from the feature map (same kernel as the
+                # unfused path; only reached when the trunks are trained)
+                argmax = torch.empty((B, C), device=fmap3.device, dtype=torch.int32)
+                scratch = torch.empty((B, C), device=fmap3.device, dtype=torch.float32)
+                _check(_lib.mgnns_rowmax_f32(fmap3.data_ptr(), B * C, P, scratch.data_ptr(), argmax.data_ptr(), _stream()),
+                       "rowmax")
             _check(_lib.mgnns_rowmax_bwd_f32(g_pooled.data_ptr(), argmax.data_ptr(), B * C, P, g_f.data_ptr(),
                                              _stream()), "rowmax_bwd")
         g_f = g_f.reshape(ctx.fshape)
