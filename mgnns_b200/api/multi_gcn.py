@@ -434,7 +434,9 @@ class Multi_GCN_Multihead_Att(nn.Module):
             return None
         pool = self.__dict__.get('_branch_pool')
         if pool is None or pool[0] != dev or len(pool[1]) < n:
-            pool = (dev, [torch.cuda.Stream(device=dev) for _ in range(n)])
+            # the first side stream carries the LSTM chain (latency-bound, leaves most SMs idle): high priority, so
+            # its CTAs are placed first and the dynamically scheduled tensor-core kernels fill the rest of the GPU
+            pool = (dev, [torch.cuda.Stream(device=dev, priority=(-1 if i == 0 else 0)) for i in range(n)])
             self.__dict__['_branch_pool'] = pool
             # gc1/gc2 are shared by the object and place channels: their AccumulateGrad nodes see gradients from
             # two streams by design

@@ -99,6 +99,57 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn_ma
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------------------------- dynamic tile scheduler
+// Persistent CTAs draw work items from a global counter instead of a static stride, so a CTA that gets its SM
+// late (another stream's kernel — the LSTM recurrence — still holds it) simply takes fewer items and the kernel
+// ends when the work does, not when the unluckiest CTA has finished a fixed share.  One thread (the TMA
+// producer) fetches the next item with atomicAdd and publishes it through a small shared-memory ring guarded by
+// mbarriers; the MMA issuer, the splitter warps and the epilogue warps consume it in order.
+constexpr int SCHED_SLOTS = 4;
+constexpr int SCHED_CONSUMERS = 9;           // MMA thread + 4 splitter warps + 4 epilogue warps
+struct SchedSmem {
+    uint64_t full[SCHED_SLOTS];
+    uint64_t empty[SCHED_SLOTS];
+    int item[SCHED_SLOTS];
+};
+struct SchedState {
+    int slot = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() { if (++slot == SCHED_SLOTS) { slot = 0; phase ^= 1; } }
+};
+__device__ __forceinline__ void sched_init(SchedSmem* sm) {
+    for (int i = 0; i < SCHED_SLOTS; ++i) {
+        mbar_init(&sm->full[i], 1);
+        mbar_init(&sm->empty[i], SCHED_CONSUMERS);
+    }
+}
+// producer thread: next item (values >= n_items tell every role to stop)
+__device__ __forceinline__ int sched_produce(SchedSmem* sm, SchedState& st, int* counter) {
+    mbar_wait(&sm->empty[st.slot], st.phase ^ 1);
+    const int item = atomicAdd(counter, 1);
+    sm->item[st.slot] = item;
+    mbar_arrive(&sm->full[st.slot]);         // release: the store above is visible to the waiters
+    st.advance();
+    return item;
+}
+// a single consumer thread (the MMA issuer)
+__device__ __forceinline__ int sched_consume_thread(SchedSmem* sm, SchedState& st) {
+    mbar_wait(&sm->full[st.slot], st.phase);
+    const int item = sm->item[st.slot];
+    mbar_arrive(&sm->empty[st.slot]);
+    st.advance();
+    return item;
+}
+// a whole consumer warp: every lane reads the item, one lane releases the slot
+__device__ __forceinline__ int sched_consume_warp(SchedSmem* sm, SchedState& st, int lane) {
+    mbar_wait(&sm->full[st.slot], st.phase);
+    const int item = sm->item[st.slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm->empty[st.slot]);
+    st.advance();
+    return item;
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -132,6 +183,9 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     MG_REQUIRE(rc == CUDA_SUCCESS, "tc_gemm: cuTensorMapEncodeTiled failed with code %d", (int)rc);
     return 0;
 }
+
+// one work counter per in-flight launch: a ring of device ints, zeroed on the launch stream before the kernel
+int* next_tile_counter(cudaStream_t st);
 
 static int sm_count() {
     static int n = 0;

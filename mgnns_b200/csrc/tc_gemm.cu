@@ -19,6 +19,7 @@
 // representable in tf32) and write lo = x - hi to a second buffer; the issuer accumulates
 // hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator, which restores ~2^-21 relative accuracy
 // (fp32-class) at three times the tensor work.
+#include <atomic>
 #include "tc_common.cuh"
 
 namespace mgnns {
@@ -43,6 +44,7 @@ struct Params {
     int n_items;                         // FWD: ceil(B * bps / 4);   DW: c_tiles * groups
     int bps;                             // FWD: 32-position boxes per sample, ceil(P/32)
     uint32_t* pooled_ord;                // FWD + SPLIT: [B,C] running spatial max as order-preserving uints (or NULL)
+    int* counter;                        // dynamic tile scheduler: next work item (zeroed before the launch)
     int groups, samples_per_group;       // DW
 };
 
@@ -67,7 +69,7 @@ struct Cfg {
     using G = Geo<PROBLEM>;
     static constexpr int STAGE_BYTES = (G::A_BYTES + G::B_BYTES) * (SPLIT ? 2 : 1);
     static constexpr int STAGES = (226 * 1024 - 1024) / STAGE_BYTES >= 4 ? 4 : (226 * 1024 - 1024) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scheduler ring*/;
 };
 
 template <int PROBLEM, bool SPLIT>
@@ -88,6 +90,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = bars + 3 * STAGES;     // accumulator complete
     uint64_t* tmem_empty = tmem_full + 1;        // accumulator drained by the epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    SchedSmem* sched = reinterpret_cast<SchedSmem*>(smem + STAGES * CF::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -108,6 +111,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 4);
+        sched_init(sched);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -131,7 +135,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            SchedState ss;
+            for (;;) {
+                const int item = sched_produce(sched, ss, p.counter);
+                if (item >= p.n_items) break;
                 const int kiters = item_kiters(item);
                 for (int kk = 0; kk < kiters; ++kk) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -186,7 +193,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t B_PART1 = G::B_MN ? (G::N0 / 32) * 4096 : G::N0 * 128;
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            SchedState ss;
+            for (;;) {
+                const int item = sched_consume_thread(sched, ss);
+                if (item >= p.n_items) break;
                 const int kiters = item_kiters(item);
                 mbar_wait(tmem_empty, tphase ^ 1);
                 tc_fence_after();
@@ -224,14 +234,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================== operand splitter (3xTF32 only)
-        if (SPLIT) {
+        {
             const int t = threadIdx.x - 128;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t pool_o[8];
             int pool_smp[4], pool_lim[4], pool_c0 = 0;
             bool pool_pending = false;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            SchedState ss;
+            for (;;) {
+                const int item = sched_consume_warp(sched, ss, lane);
+                if (item >= p.n_items) break;
+                if (!SPLIT) continue;                    // plain TF32: nothing to split, only keep the scheduler ring moving
                 const int kiters = item_kiters(item);
                 if (PROBLEM == FWD && p.pooled_ord != nullptr) {
 #pragma unroll
@@ -328,7 +342,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                          // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         uint32_t tphase = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        SchedState ss;
+        for (;;) {
+            const int item = sched_consume_warp(sched, ss, lane);
+            if (item >= p.n_items) break;
             mbar_wait(tmem_full, tphase);
             tc_fence_after();
             const int kiters = item_kiters(item);
@@ -393,6 +410,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
+// ring of work counters for the dynamic tile scheduler (tc_common.cuh)
+__device__ int g_tile_counters[256];
+
+int* next_tile_counter(cudaStream_t st) {
+    static int* base = nullptr;
+    static std::atomic<unsigned> next{0};
+    if (!base) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_tile_counters) != cudaSuccess) return nullptr;
+        base = static_cast<int*>(ptr);
+    }
+    int* c = base + (next.fetch_add(1, std::memory_order_relaxed) % 256u);
+    if (cudaMemsetAsync(c, 0, sizeof(int), st) != cudaSuccess) return nullptr;
+    return c;
+}
+
 // order-preserving uint -> float, in place (the fused max pool accumulates with integer atomicMax)
 __global__ void ordered_to_float_kernel(uint32_t* __restrict__ v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,7 +460,10 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
     }
     int grid = sm_count();
     if (grid > p.n_items) grid = p.n_items;
-    tc_gemm_kernel<PROBLEM, SPLIT><<<grid, NTHREADS, CF::SMEM_BYTES, st>>>(a, b, blo, p);
+    Params q = p;
+    q.counter = next_tile_counter(st);
+    MG_REQUIRE(q.counter != nullptr, "tc_gemm: cannot set up the tile counter");
+    tc_gemm_kernel<PROBLEM, SPLIT><<<grid, NTHREADS, CF::SMEM_BYTES, st>>>(a, b, blo, q);
     MG_LAUNCH_CHECK("tc_gemm");
     return 0;
 }
@@ -526,7 +562,9 @@ extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B,
     p.B = B; p.C = C; p.P = P; p.O = O;
     p.bias = nullptr; p.out = gW;
     const int c_tiles = (C + 127) / 128;
-    int groups = sm_count() / c_tiles;
+    // about four work items per CTA: the dynamic scheduler then absorbs CTAs that get their SM late (a concurrent
+    // kernel of another stream) at the price of 4x the epilogue atomics (still < 5 % of an item's MMA time)
+    int groups = 4 * sm_count() / c_tiles;
     if (groups < 1) groups = 1;
     if (groups > B) groups = B;
     p.groups = groups;

@@ -39,13 +39,14 @@ struct LinParams {
     float* C;
     int64_t ldc;
     int n_tiles, BN, k_chunks, n_items;
+    int* counter;                          // dynamic tile scheduler: next work item (zeroed before the launch)
 };
 
 template <bool SPLIT>
 struct LinCfg {
     static constexpr int STAGE_BYTES = (L_A_BYTES + L_B_BYTES) * (SPLIT ? 2 : 1);
     static constexpr int STAGES = SPLIT ? 2 : 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scheduler ring*/;
 };
 
 template <bool SPLIT, bool B_MN>
@@ -63,6 +64,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = bars + 3 * STAGES;     // [2] accumulator complete
     uint64_t* tmem_empty = tmem_full + 2;        // [2] accumulator drained by the epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    SchedSmem* sched = reinterpret_cast<SchedSmem*>(smem + STAGES * CF::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -87,6 +89,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
         }
+        sched_init(sched);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -95,10 +98,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // contiguous range of work items (n tile fastest: the A row tile is re-read from L2 right away)
-    const int per = (p.n_items + gridDim.x - 1) / gridDim.x;
-    const int item0 = blockIdx.x * per;
-    const int item1 = min(p.n_items, item0 + per);
+    // work items (n tile fastest: the A row tile is re-read from L2 right away) come from the dynamic scheduler
     const int BN = p.BN;
 
     if (warp == 0) {
@@ -107,7 +107,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = L_A_BYTES + (uint32_t)BN * 128u * (SPLIT ? 2u : 1u);
-            for (int item = item0; item < item1; ++item) {
+            SchedState ss;
+            for (;;) {
+                const int item = sched_produce(sched, ss, p.counter);
+                if (item >= p.n_items) break;
                 const int mt = item / p.n_tiles, nt = item - mt * p.n_tiles;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -138,8 +141,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t B_LT = B_MN ? 1 : 2;
             int stage = 0;
             uint32_t phase = 0, tphase[2] = {0, 0};
-            for (int item = item0; item < item1; ++item) {
-                const int ab = (item - item0) & 1;
+            SchedState ss;
+            for (int it = 0;; ++it) {
+                const int item = sched_consume_thread(sched, ss);
+                if (item >= p.n_items) break;
+                const int ab = it & 1;
                 const uint32_t tacc = tmem_base + (uint32_t)ab * L_BN_MAX;
                 mbar_wait(&tmem_empty[ab], tphase[ab] ^ 1);
                 tc_fence_after();
@@ -171,11 +177,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================== operand splitter (3xTF32: A only)
-        if (SPLIT) {
+        {
             const int t = threadIdx.x - 128;
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = item0; item < item1; ++item) {
+            SchedState ss;
+            for (;;) {
+                const int item = sched_consume_warp(sched, ss, lane);
+                if (item >= p.n_items) break;
+                if (!SPLIT) continue;                    // plain TF32: only keep the scheduler ring moving
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&full[stage], phase);
                     float4* hi = reinterpret_cast<float4*>(stageA(stage));
@@ -206,8 +216,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = q * 32 + lane;
         uint32_t tphase[2] = {0, 0};
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
-        for (int item = item0; item < item1; ++item) {
-            const int ab = (item - item0) & 1;
+        SchedState ss;
+        for (int it = 0;; ++it) {
+            const int item = sched_consume_warp(sched, ss, lane);
+            if (item >= p.n_items) break;
+            const int ab = it & 1;
             const int mt = item / p.n_tiles, nt = item - mt * p.n_tiles;
             mbar_wait(&tmem_full[ab], tphase[ab]);
             tc_fence_after();
@@ -281,7 +294,10 @@ static int launch_linear(const CUtensorMap& a, const CUtensorMap& bhi, const CUt
     }
     int grid = sm_count();
     if (grid > p.n_items) grid = p.n_items;
-    tc_linear_kernel<SPLIT, B_MN><<<grid, L_THREADS, CF::SMEM_BYTES, st>>>(a, bhi, blo, p);
+    LinParams q = p;
+    q.counter = next_tile_counter(st);
+    MG_REQUIRE(q.counter != nullptr, "linear_tc: cannot set up the tile counter");
+    tc_linear_kernel<SPLIT, B_MN><<<grid, L_THREADS, CF::SMEM_BYTES, st>>>(a, bhi, blo, q);
     MG_LAUNCH_CHECK("linear_tc");
     return 0;
 }
