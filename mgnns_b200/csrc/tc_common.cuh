@@ -1,6 +1,7 @@
 // Shared tcgen05 / TMEM / TMA plumbing for the tensor-core translation units (sm_100a).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mgnns {
@@ -186,6 +187,19 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 
 // one work counter per in-flight launch: a ring of device ints, zeroed on the launch stream before the kernel
 int* next_tile_counter(cudaStream_t st);
+
+// CTAs a persistent tensor-core kernel launches: all SMs unless MGNNS_TC_CTAS caps it (leaving SMs to the small
+// latency-bound kernels of concurrent streams; the dynamic scheduler makes the grid size a free parameter)
+static int sm_count();
+static int tc_grid_limit() {
+    static int n = 0;
+    if (!n) {
+        const char* v = getenv("MGNNS_TC_CTAS");
+        n = v ? atoi(v) : 0;
+        if (n <= 0 || n > sm_count()) n = sm_count();
+    }
+    return n;
+}
 
 static int sm_count() {
     static int n = 0;

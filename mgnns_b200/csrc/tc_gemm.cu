@@ -458,7 +458,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
                    cudaGetErrorString(e));
         configured = true;
     }
-    int grid = sm_count();
+    int grid = tc_grid_limit();
     if (grid > p.n_items) grid = p.n_items;
     Params q = p;
     q.counter = next_tile_counter(st);

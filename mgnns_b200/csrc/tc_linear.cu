@@ -292,7 +292,7 @@ static int launch_linear(const CUtensorMap& a, const CUtensorMap& bhi, const CUt
                    cudaGetErrorString(e));
         configured = true;
     }
-    int grid = sm_count();
+    int grid = tc_grid_limit();
     if (grid > p.n_items) grid = p.n_items;
     LinParams q = p;
     q.counter = next_tile_counter(st);
