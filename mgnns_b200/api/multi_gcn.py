@@ -240,7 +240,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
             self.embedding.weight.data = torch.Tensor(weights)
         self.embedding.weight.data[pad_idx] = 0
 
-    def get_text_memory_bank(self, text, text_lens, return_last_state=True):
+    def get_text_memory_bank(self, text, text_lens, return_last_state=True, after_first_projection=None):
         """Embedding -> 2-layer bi-LSTM over the valid tokens only -> zero-padded bank [B,L,300]
         (ref: model:366-398: pack_padded_sequence + cuDNN LSTM + pad_packed_sequence).  The recurrence
         runs in mgnns::lstm_rec over compacted tokens; nn.LSTM only holds the parameters."""
@@ -249,7 +249,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
         plan = self.make_text_plan(text_lens, max_text_len)
         tokens = text.to(dev).reshape(-1).index_select(0, plan.tok_idx)
         text_embed = self.embedding(tokens)                                        # [N, emb]
-        y = ops.packed_bilstm(self.lstm, text_embed, plan, self.training)          # [N, 2H]
+        y = ops.packed_bilstm(self.lstm, text_embed, plan, self.training, after_first_projection)   # [N, 2H]
         # scatter back to the padded layout; plan padding rows land in one dummy row that is sliced off
         memory_bank = y.new_zeros(batch_size * max_text_len + 1, y.shape[1]).index_copy(0, plan.flat_idx, y)
         memory_bank = memory_bank[:batch_size * max_text_len].view(batch_size, max_text_len, y.shape[1])
@@ -342,8 +342,8 @@ class Multi_GCN_Multihead_Att(nn.Module):
         def text_gcn():
             return self.text_features(text)                                           # [B, 300]
 
-        def text_bank():
-            return self.get_text_memory_bank(text, text_lens, True)[0]                # [B, L, 300]
+        def text_bank(hook=None):
+            return self.get_text_memory_bank(text, text_lens, True, hook)[0]          # [B, L, 300]
 
         def object_channel():
             self.object_feature = self.object_features(object_feature)                # [B, 2048, 14, 14]
@@ -382,15 +382,24 @@ class Multi_GCN_Multihead_Att(nn.Module):
             main, (s_txt, s_obj, s_plc) = streams
             for side in (s_txt, s_obj, s_plc):
                 side.wait_stream(main)                      # fork: after everything already enqueued on main
+            # The LSTM recurrence is latency-bound and leaves most SMs idle, while the image-bank kernels are
+            # persistent and take every SM they can get: the image channels therefore start once the LSTM's first
+            # input projection is done, i.e. when the recurrence is being launched on its high-priority stream, so
+            # the recurrence gets its SMs first and the (dynamically scheduled) tensor-core kernels fill the rest.
+            lstm_ready = []
+            with torch.cuda.stream(s_txt):
+                text_memory_bank = text_bank(lambda: lstm_ready.append(s_txt.record_event()))
+                ev_bank = s_txt.record_event()
             with torch.cuda.stream(s_obj):
+                for ev in lstm_ready:
+                    s_obj.wait_event(ev)
                 img_object_memory_bank, object_x_attention = object_channel()
                 ev_obj = s_obj.record_event()
             with torch.cuda.stream(s_plc):
+                for ev in lstm_ready:
+                    s_plc.wait_event(ev)
                 img_place_memory_bank, place_x_attention = place_channel()
                 ev_plc = s_plc.record_event()
-            with torch.cuda.stream(s_txt):
-                text_memory_bank = text_bank()
-                ev_bank = s_txt.record_event()
             text_feature = text_gcn()
             ev_tf = main.record_event()
             with torch.cuda.stream(s_obj):

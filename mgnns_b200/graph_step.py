@@ -89,7 +89,12 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         logits = self.model(b['text'], self.lens_key, b['mask'], b['fo'], b['fp'], b['oinp'], b['pinp'])
         loss = self.crit(logits, b['labels'])
-        loss.backward()
+        prev = ops.defer_weight_grads(True)      # many-row weight gradients leave the critical path (ops.py)
+        try:
+            loss.backward()
+        finally:
+            ops.defer_weight_grads(prev)
+            ops.join_deferred()                  # ... and are joined before anything reads .grad
         return loss.detach()
 
     def _clip_and_step(self):

@@ -89,6 +89,60 @@ class _timed:
         return False
 
 
+# ----------------------------------------------------------------------------- deferred weight gradients
+# The gradient of a weight is not needed before the optimizer, but autograd computes it inline, in the middle of
+# the chain that produces the gradient the NEXT layer is waiting for (LSTM layer 2 -> layer 1: three many-row
+# products, ~0.5 ms per layer on the critical path).  With deferral on, the LSTM weight-gradient products are
+# enqueued on a side stream (they overlap the latency-bound recurrence of the next layer), autograd is handed None
+# for those parameters, and join_deferred() — called after loss.backward() — joins the side stream and adds the
+# results to .grad.  Opt-in (GraphedTrainStep does both); gradients are identical to the inline path.
+_defer_state = {"enabled": False, "streams": {}, "pending": []}
+
+
+def defer_weight_grads(enabled: bool) -> bool:
+    prev, _defer_state["enabled"] = _defer_state["enabled"], bool(enabled)
+    return prev
+
+
+def _defer_stream(device):
+    s = _defer_state["streams"].get(device)
+    if s is None:
+        s = _defer_state["streams"][device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _run_deferred(fn, inputs, params):
+    """Enqueue fn() -> list of gradient tensors (one per entry of `params`, None allowed) on the side stream, after
+    everything enqueued so far on the current stream; the (param, grad) pairs are applied by join_deferred()."""
+    dev = inputs[0].device
+    cur = torch.cuda.current_stream(dev)
+    side = _defer_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        grads = fn()
+    for t in inputs:
+        t.record_stream(side)
+    for p, g in zip(params, grads):
+        if p is not None and g is not None:
+            _defer_state["pending"].append((p, g))
+
+
+def join_deferred():
+    """Join the deferred weight-gradient stream into the current one and accumulate the results into .grad
+    (call after loss.backward(), before anything reads the gradients)."""
+    pending, _defer_state["pending"] = _defer_state["pending"], []
+    devs = {g.device for _, g in pending}
+    for dev in devs:
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(_defer_stream(dev))
+    for p, g in pending:
+        g.record_stream(torch.cuda.current_stream(g.device))
+        if p.grad is None:
+            p.grad = g
+        else:
+            p.grad = p.grad + g
+
+
 # ----------------------------------------------------------------------------- helpers
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
@@ -993,6 +1047,7 @@ def _lstm_setup(ctx, inputs, output):
     g, whh_f, whh_r, offsets, lens, tiles, n_tiles = inputs
     ctx.save_for_backward(whh_f, whh_r, offsets, lens, tiles, output[1], output[2], output[3])
     ctx.n_tiles = n_tiles
+    ctx.whh_leaves = (whh_f, whh_r)        # the parameter objects themselves (deferred weight gradients)
 
 
 def _lstm_backward(ctx, gy, ggates, gc, ghp):
@@ -1007,19 +1062,67 @@ def _lstm_backward(ctx, gy, ggates, gc, ghp):
         _check(_lib.mgnns_lstm_rec_bwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), ctx.n_tiles, H,
                                        gy.data_ptr(), gates.data_ptr(), csave.data_ptr(), whh_f.data_ptr(),
                                        whh_r.data_ptr(), dG.data_ptr(), _stream()), "lstm_rec_bwd")
+    need_f, need_r = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+
+    def weight_grads():
+        g_f_ = g_r_ = None
+        if need_f:
+            g_f_ = _mm_impl(dG[:, :4 * H], hprev[:, 0, :], None, True, False, ACT_NONE, 0.0)      # dWhh = dG^T . Hprev
+        if need_r:
+            g_r_ = _mm_impl(dG[:, 4 * H:], hprev[:, 1, :], None, True, False, ACT_NONE, 0.0)
+        return [g_f_, g_r_]
+
     g_f = g_r = None
-    mm = torch.ops.mgnns.mm
-    if ctx.needs_input_grad[1]:
-        g_f = mm(dG[:, :4 * H], hprev[:, 0, :], None, True, False, ACT_NONE, 0.0)      # dWhh = dG^T . Hprev
-    if ctx.needs_input_grad[2]:
-        g_r = mm(dG[:, 4 * H:], hprev[:, 1, :], None, True, False, ACT_NONE, 0.0)
+    if _defer_state["enabled"] and ctx.whh_leaves[0].is_leaf and ctx.whh_leaves[1].is_leaf:
+        _run_deferred(weight_grads, (dG, hprev), ctx.whh_leaves)
+    else:
+        g_f, g_r = weight_grads()
     return (dG if ctx.needs_input_grad[0] else None), g_f, g_r, None, None, None, None
 
 
 torch.library.register_autograd("mgnns::lstm_rec", _lstm_backward, setup_context=_lstm_setup)
 
 
-def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, training: bool):
+class _LstmInputProjection(torch.autograd.Function):
+    """G[N, 8H] = x . [W_ih_fwd; W_ih_rev]^T + (b_ih + b_hh) for both directions in one many-row product
+    (ref: the input half of nn.LSTM, model:179-184,:378).  A Function over the leaf parameters (not cat + mm) so
+    that backward can hand the four weight/bias gradients to the deferred stream and return None for them."""
+
+    @staticmethod
+    def forward(ctx, x, w_f, w_r, bih_f, bhh_f, bih_r, bhh_r):
+        W = torch.cat([w_f, w_r], 0)
+        bias = None if bih_f is None else torch.cat([bih_f + bhh_f, bih_r + bhh_r], 0)
+        ctx.save_for_backward(x, W)
+        ctx.leaves = (w_f, w_r, bih_f, bhh_f, bih_r, bhh_r)
+        return _mm_impl(x, W, bias, False, True, ACT_NONE, 0.0)
+
+    @staticmethod
+    def backward(ctx, dG):
+        x, W = ctx.saved_tensors
+        w_f, w_r, bih_f, bhh_f, bih_r, bhh_r = ctx.leaves
+        dG = _f32c(dG, "grad")
+        H4 = W.shape[0] // 2
+        gx = _mm_impl(dG, W, None, False, False, ACT_NONE, 0.0) if ctx.needs_input_grad[0] else None
+        need = ctx.needs_input_grad
+
+        def weight_grads():
+            gf = _mm_impl(dG[:, :H4], x, None, True, False, ACT_NONE, 0.0) if need[1] else None
+            gr = _mm_impl(dG[:, H4:], x, None, True, False, ACT_NONE, 0.0) if need[2] else None
+            out = [gf, gr, None, None, None, None]
+            if bih_f is not None:
+                bf, br = colsum(dG[:, :H4]), colsum(dG[:, H4:])
+                out[2:] = [bf if need[3] else None, bf.clone() if need[4] else None,
+                           br if need[5] else None, br.clone() if need[6] else None]
+            return out
+
+        leaves_ok = all(p is None or p.is_leaf for p in ctx.leaves)
+        if _defer_state["enabled"] and leaves_ok:
+            _run_deferred(weight_grads, (dG, x), ctx.leaves)
+            return (gx, None, None, None, None, None, None)
+        return (gx, *weight_grads())
+
+
+def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, training: bool, after_first_projection=None):
     """Multi-layer bidirectional LSTM over compacted tokens with nn.LSTM's parameters (same names, same
     math as torch's packed-sequence path, inter-layer dropout included).  Returns [N, 2H]."""
     if not lstm.bidirectional or not lstm.batch_first or lstm.proj_size != 0:
@@ -1027,15 +1130,18 @@ def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, 
     x = x_compact
     for layer in range(lstm.num_layers):
         sfx = "_l%d" % layer
-        w_ih = torch.cat([getattr(lstm, "weight_ih" + sfx), getattr(lstm, "weight_ih" + sfx + "_reverse")], 0)
+        P = lambda name: getattr(lstm, name + sfx)                     # noqa: E731
+        R = lambda name: getattr(lstm, name + sfx + "_reverse")        # noqa: E731
         if lstm.bias:
-            b = torch.cat([getattr(lstm, "bias_ih" + sfx) + getattr(lstm, "bias_hh" + sfx),
-                           getattr(lstm, "bias_ih" + sfx + "_reverse") + getattr(lstm, "bias_hh" + sfx + "_reverse")], 0)
+            biases = (P("bias_ih"), P("bias_hh"), R("bias_ih"), R("bias_hh"))
         else:
-            b = None
-        g = torch.ops.mgnns.mm(x, w_ih, b, False, True, ACT_NONE, 0.0)                      # [N, 8H]
-        y = torch.ops.mgnns.lstm_rec(g, getattr(lstm, "weight_hh" + sfx), getattr(lstm, "weight_hh" + sfx + "_reverse"),
-                                     plan.offsets, plan.lens, plan.tiles, plan.n_tiles)[0]
+            biases = (None, None, None, None)
+        _need_cuda(x)
+        x = _f32c(x, "x")
+        g = _LstmInputProjection.apply(x, P("weight_ih"), R("weight_ih"), *biases)                  # [N, 8H]
+        if layer == 0 and after_first_projection is not None:
+            after_first_projection()      # e.g. record an event: the (SM-hungry) recurrence is about to be enqueued
+        y = torch.ops.mgnns.lstm_rec(g, P("weight_hh"), R("weight_hh"), plan.offsets, plan.lens, plan.tiles, plan.n_tiles)[0]
         if layer + 1 < lstm.num_layers and training and lstm.dropout > 0:
             y = torch.nn.functional.dropout(y, lstm.dropout, True)
         x = y

@@ -73,3 +73,16 @@ print("time with N activities in flight: " + ", ".join("%d: %.2f ms" % (k, v / 1
 print("\n%-62s %10s %10s" % ("kernel", "total us", "alone us"))
 for k, v in sorted(total.items(), key=lambda kv: -alone.get(kv[0], 0))[:28]:
     print("%-62s %10.1f %10.1f" % (k, v, alone.get(k, 0.0)))
+
+# compact Gantt of the long activities (>= 40 us) and of every stream's busy span
+print("\nstart_ms  end_ms  stream  kernel")
+for e in step:
+    if e['dur'] >= 40:
+        print("%7.3f %7.3f  %6s  %s" % ((e['ts'] - t0) / 1e3, (e['ts'] + e['dur'] - t0) / 1e3, e['args'].get('stream'), e['name'][:70]))
+by_stream = defaultdict(list)
+for e in step:
+    by_stream[e['args'].get('stream')].append(e)
+print("\nstream: first start, last end, busy ms, activities")
+for sid, evs in sorted(by_stream.items(), key=lambda kv: kv[1][0]['ts']):
+    print("%6s  %7.3f %7.3f  %6.3f  %d" % (sid, (evs[0]['ts'] - t0) / 1e3, (max(x['ts'] + x['dur'] for x in evs) - t0) / 1e3,
+                                             sum(x['dur'] for x in evs) / 1e3, len(evs)))

@@ -690,6 +690,40 @@ def test_branch_streams_match_single_stream(dev, golden):
         close(out[True][1][n], g, 1e-4, 1e-6, msg=n)
 
 
+def test_deferred_lstm_weight_grads_match_inline(dev, ops, golden):
+    """ops.defer_weight_grads: the LSTM weight-gradient products run on a side stream and are added to .grad by
+    join_deferred(); every gradient must equal the inline autograd path (same kernels, same operands)."""
+    zp = golden('pmi_synth300.npz')
+    cfg = dict(H.MODEL_CFG, B=12)
+    model = build_model(dev, cfg, H.edge_map_from_golden(zp, cfg['V']), int(zp['count'])).eval()
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    args = (text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    grads = {}
+    for defer in (False, True):
+        for streams in (False, True):
+            model.branch_streams = streams
+            for _ in range(2):
+                model.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.cross_entropy(model(*args), labels.to(dev))
+                prev = ops.defer_weight_grads(defer)
+                try:
+                    loss.backward()
+                finally:
+                    ops.defer_weight_grads(prev)
+                    ops.join_deferred()
+            torch.cuda.synchronize()
+            grads[(defer, streams)] = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    base = grads[(False, False)]
+    lstm_names = [n for n in base if n.startswith('lstm.')]
+    assert len(lstm_names) == 16
+    for key, g in grads.items():
+        assert g.keys() == base.keys(), key
+        for n in lstm_names:
+            assert torch.equal(g[n], base[n]), (key, n)          # deterministic split-K products: bitwise equal
+        for n in base:
+            close(g[n], base[n], 1e-4, 1e-6, msg=str((key, n)))
+
+
 def test_full_model_bigger_batch_vs_oracle_and_mvsa_labels(dev):
     """B=24 against the CPU oracle on a fresh seed, 7 and 3 labels (MVSA-shaped)."""
     for num_labels, seed in ((7, 23), (3, 24)):
