@@ -194,6 +194,13 @@ int mgnns_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, in
                     const float* bias, int act, float slope, int M, int N, int K, int precision,
                     float* workspace, int64_t workspace_floats, float* C, int64_t ldc, void* stream);
 
+/* Weight-gradient product on the tensor cores:  C[M,N] = A[K,M]^T . B[K,N]  with a long reduction (K = rows of
+ * a batch / tokens).  A and B are row-major with the reduction index as the row (lda, ldb multiples of 4, 16-byte
+ * aligned); C is overwritten.  K slices are accumulated with fp32 atomics (summation order varies run to run).
+ * ref: the dW that autograd computes for nn.LSTM's projections (model:179-184) and the many-row nn.Linear layers */
+int mgnns_wgrad_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K, int precision,
+                   float* C, int64_t ldc, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Image-bank contraction on the tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  *   fwd: bank[b,p,o] = sum_c fmap[b,c,p] * weight[o,c] + bias[o]

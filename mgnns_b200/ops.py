@@ -231,6 +231,7 @@ def _mm_shapes(a, b, trans_a, trans_b):
 _gemm = _lib.mgnns_gemm_f32
 _linear_tc = _lib.mgnns_linear_tc
 _linear_tc_ws = _lib.mgnns_linear_tc_workspace
+_wgrad_tc = _lib.mgnns_wgrad_tc
 _TC_MIN_ROWS = int(os.environ.get("MGNNS_TC_MIN_ROWS", "2048"))   # below this the 128-row tiles cannot fill 148 SMs
 _gemm_ws = _lib.mgnns_gemm_f32_ws
 _f32 = torch.float32
@@ -286,6 +287,15 @@ def _mm_impl(a, b, bias, trans_a, trans_b, act, slope):
                             ws.data_ptr(), wsf, c.data_ptr(), N, _raw_stream(a.device.index))
         if rc:
             _check(rc, "linear_tc")
+        return c
+    if (prec is not None and trans_a and not trans_b and K >= _TC_MIN_ROWS and a.stride(0) % 4 == 0 and b.stride(0) % 4 == 0
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and bp is None and act == ACT_NONE):
+        # weight-gradient shape (reduction over many rows): tcgen05 kernel with split-K atomics
+        with _timed("wgrad_tc"):
+            rc = _wgrad_tc(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, prec, c.data_ptr(), N,
+                           _raw_stream(a.device.index))
+        if rc:
+            _check(rc, "wgrad_tc")
         return c
     ws_floats = 0 if trans_a else _ws_size(M, N, K)
     if ws_floats:
@@ -1066,6 +1076,12 @@ def _lstm_backward(ctx, gy, ggates, gc, ghp):
 
     def weight_grads():
         g_f_ = g_r_ = None
+        if need_f and need_r and _PRECISIONS[_precision] is not None and N >= _TC_MIN_ROWS and (2 * H) % 4 == 0:
+            # one tensor-core product dG^T . [Hprev_fwd | Hprev_rev] -> [8H, 2H]; the two diagonal blocks are the
+            # gradients (the reverse half of Hprev alone starts at a non-16-byte-aligned address, which TMA rejects;
+            # the off-diagonal flops are cheaper than two CUDA-core products)
+            full = _mm_impl(dG, hprev.view(N, 2 * H), None, True, False, ACT_NONE, 0.0)
+            return [full[:4 * H, :H].contiguous(), full[4 * H:, H:].contiguous()]
         if need_f:
             g_f_ = _mm_impl(dG[:, :4 * H], hprev[:, 0, :], None, True, False, ACT_NONE, 0.0)      # dWhh = dG^T . Hprev
         if need_r:
