@@ -147,3 +147,73 @@ def test_optimizer_groups_omit_the_never_stepped_parameters():
     for n in ('gc1.weight', 'lstm.weight_ih_l0', 'text_features.node_hidden.weight',
               'img_object_text_multi_head_att.0.slf_attn.w_qs.weight', 'object_attention.w_q.weight'):
         assert id(named[n]) in stepped, n
+
+
+def test_lstm_plan_host_schedule_sorted_tiles_and_compact_indices():
+    """Host-side schedule of the packed bi-LSTM (ref: pack_padded_sequence at model:376): compact rows, length-sorted
+    tiles of 8, first/last token rows, fixed-capacity refresh for CUDA-graph replays."""
+    from mgnns_b200 import ops
+    lens = torch.tensor([3, 0, 7, 1, 100, 5, 2, 2, 9, 4], dtype=torch.int64)
+    L = 100
+    plan = ops.LstmPlan(lens, L, torch.device('cpu'), capacity=256)
+    n = int(lens.sum())
+    assert plan.N == n and plan.capacity == 256 and plan.n_tiles == 2
+    off = plan.offsets.numpy()
+    assert off[0] == 0 and off[-1] == n and np.array_equal(np.diff(off), lens.numpy())
+    tiles = plan.tiles.numpy()
+    order = tiles[tiles >= 0]
+    assert sorted(order.tolist()) == [i for i in range(10) if lens[i] > 0]           # empty sequences are skipped
+    assert np.all(np.diff(lens.numpy()[order]) <= 0)                                  # longest first
+    tok = plan.tok_idx.numpy()[:n]
+    rows = np.repeat(np.arange(10), lens.numpy())
+    assert np.array_equal(tok // L, rows) and np.array_equal(tok % L, np.arange(n) - off[rows])
+    assert np.all(plan.flat_idx.numpy()[n:] == 10 * L)                                # padding rows -> dummy bank row
+    assert np.array_equal(plan.last_idx.numpy()[lens.numpy() > 0], (off[1:] - 1)[lens.numpy() > 0])
+    plan.update_(torch.tensor([1] * 10, dtype=torch.int64))                           # refresh in place, same capacity
+    assert plan.N == 10 and plan.capacity == 256 and int(plan.offsets[-1]) == 10
+    with pytest.raises(RuntimeError):
+        ops.LstmPlan(torch.tensor([100, 100, 100]), L, torch.device('cpu'), capacity=256)
+
+
+def test_cfg2_word_graph_and_csr_transpose_on_host():
+    """SURVEY §8d cfg-2 adjacency generator: self loops, sorted unique columns, rows normalised to 1; and the host CSR
+    transpose used by the backward SpMM."""
+    from mgnns_b200.api.graph_util import CSRAdjacency
+    N = 300
+    rowptr, cols, val = synth.cfg2_word_graph(N, mean_degree=10, seed=2)
+    assert rowptr[0] == 0 and rowptr[-1] == cols.shape[0] == val.shape[0]
+    for i in (0, 17, N - 1):
+        c = cols[rowptr[i]:rowptr[i + 1]]
+        assert i in c and np.all(np.diff(c) > 0)
+        np.testing.assert_allclose(val[rowptr[i]:rowptr[i + 1]].sum(), 1.0, rtol=1e-5)
+    csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, torch.device('cpu'))
+    dense = np.zeros((N, N), dtype=np.float32)
+    dense[np.repeat(np.arange(N), np.diff(rowptr)), cols] = val
+    t = np.zeros((N, N), dtype=np.float32)
+    tr, tc, tv = csr.t_rowptr.numpy(), csr.t_col.numpy(), csr.t_val.numpy()
+    t[np.repeat(np.arange(N), np.diff(tr)), tc] = tv
+    assert np.array_equal(t, dense.T) and csr.nnz == cols.shape[0]
+
+
+def test_launch_list_summariser(tmp_path, capsys):
+    """scripts/summarize_launches.py: one step = the span between the last two anchor launches."""
+    import importlib.util
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC",'
+            '"Section Name","Metric Name","Metric Unit","Metric Value"']
+    names = ['mgnns::text_maxagg_fwd_kernel(a)', 'void mgnns::gemm_ffma_kernel<1, 1>(p)', 'void at::native::foo<int>(x)'] * 3
+    for i, n in enumerate(names):
+        rows.append('"%d","1","python","h","%s","1","7","(128, 1, 1)","(10, 1, 1)","0","10.0","s","gpu__time_duration.sum","ns","%d"'
+                    % (i, n, 1000 * (i + 1)))
+    p = tmp_path / 'l.csv'
+    p.write_text("==PROF== noise\n" + "\n".join(rows) + "\n")
+    spec = importlib.util.spec_from_file_location('summ', os.path.join(ROOT, 'scripts', 'summarize_launches.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import sys
+    argv, sys.argv = sys.argv, ['summarize_launches.py', str(p)]
+    try:
+        mod.main()
+    finally:
+        sys.argv = argv
+    out = capsys.readouterr().out
+    assert 'launches [3, 6)' in out and '3 launches' in out and 'mgnns::gemm_ffma_kernel' in out
