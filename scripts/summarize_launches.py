@@ -54,8 +54,8 @@ def main():
     print("| kernel | launches | us | share |\n|---|---:|---:|---:|")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         print("| `%s` | %d | %.1f | %.1f%% |" % (k, n, t / 1e3, 100 * t / total))
-    ours = sum(t for k, (n, t) in agg.items() if 'mgnns::' in k)
-    print("\nhand-written `mgnns::` kernels: %.1f%% of the step's kernel time" % (100 * ours / total))
+    ours = sum(t for k, (n, t) in agg.items() if 'mgnns::' in k or k.startswith('tc::'))
+    print("\nhand-written kernels (`mgnns::*`, incl. `mgnns::tc::*`): %.1f%% of the step's kernel time" % (100 * ours / total))
 
 
 if __name__ == '__main__':
