@@ -83,13 +83,19 @@ __device__ __forceinline__ void ring_read(const float* slot, int D4, int lane, f
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
 }
+__device__ __forceinline__ float dot4acc(float d, const float4& a, const float4& b) {
+    d = fmaf(a.x, b.x, d); d = fmaf(a.y, b.y, d); d = fmaf(a.z, b.z, d);
+    return fmaf(a.w, b.w, d);
+}
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
     acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y);
     acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
 __device__ __forceinline__ void scale4(float4& acc, float s) { acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s; }
 
-template <int NV>
+// MASKED / DROPOUT are compile-time: the image-bank launches (no mask) and eval-mode launches (no dropout) drop the
+// live-row table, the keep table and every branch on them from the row loop, which is instruction-issue bound.
+template <int NV, bool MASKED, bool DROPOUT>
 __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask,
     int B, int H, int L, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
     }
 
     const float* bk = bank + (int64_t)b * L * D;
-    const float* mk = mask ? mask + (int64_t)b * L : nullptr;
+    const float* mk = MASKED ? mask + (int64_t)b * L : nullptr;
 
     float* myring = ring + (size_t)warp * RING * D;
     // live-row table in shared memory + the live bound Lb = 1 + last live row: padded text banks (mean 16 of
@@ -136,23 +142,23 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
     if (threadIdx.x == 0) s_lb = 0;
     for (int i = threadIdx.x; i < HG * L; i += AT_THREADS) sc[i] = -INFINITY;
     __syncthreads();
-    {
+    if (MASKED) {
         int last = 0;
         for (int l = threadIdx.x; l < L; l += AT_THREADS) {
-            const bool on = !(mk && mk[l] == 0.f);
+            const bool on = mk[l] != 0.f;
             lv[l] = on ? 1 : 0;
             if (on) last = l + 1;
         }
         last = __reduce_max_sync(0xffffffffu, last);
         if (lane == 0 && last > 0) atomicMax(&s_lb, last);
+        __syncthreads();
     }
-    __syncthreads();
-    const int Lb = s_lb;
-    auto row_live = [&](int l) { return (l < Lb) && lv[l] != 0; };
+    const int Lb = MASKED ? s_lb : L;
+    auto row_live = [&](int l) { return (l < Lb) && (!MASKED || lv[l] != 0); };
 
     // dropout keep flags for this sample's [nh, L] probabilities, computed once (the counter-based generator is
     // ~25 integer instructions; per row and lane it used to be a quarter of the kernel's instruction stream)
-    if (p_drop > 0.f) {
+    if (DROPOUT) {
         for (int i = threadIdx.x; i < nh * L; i += AT_THREADS) {
             const int h = i / L, l = i - h * L;
             kp[i] = uniform01(seed, ((uint64_t)b * H + h0 + h) * L + l) >= p_drop ? 1.f : 0.f;
@@ -168,12 +174,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
         const int l = warp + j * AT_WARPS;
         ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
     }
-    int j0 = 0;                                          // ring index of the pair's first row
-    for (int l = warp; l < Lb; l += 2 * AT_WARPS, j0 += 2) {
+    int s0 = 0;                                          // ring slot of the pair's first row: 0, 2, 4, 0, ...
+    const int full_v = D4 >> 5;                          // float4 columns that every lane owns
+    for (int l = warp; l < Lb; l += 2 * AT_WARPS) {
+        const int sp = (s0 >= 2) ? s0 - 2 : s0 + RING - 2;   // slot of the pair being prefetched (two pairs ahead)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int lp = l + (RING - 2 + r) * AT_WARPS;
-            ring_issue<NV>(myring + ((j0 + RING - 2 + r) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+            ring_issue<NV>(myring + (sp + r) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
         }
         cp_async_wait<RING - 2>();
         __syncwarp();
@@ -182,12 +190,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
         float4 k[2][NV];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            if (live[r]) ring_read<NV>(myring + ((j0 + r) % RING) * D, D4, lane, k[r]);
+            if (live[r]) ring_read<NV>(myring + (s0 + r) * D, D4, lane, k[r]);
             else {
 #pragma unroll
                 for (int v = 0; v < NV; ++v) k[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        s0 = (s0 == RING - 2) ? 0 : s0 + 2;
         float dot[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) dot[i] = 0.f;
@@ -196,10 +205,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const int c = lane + 32 * v;
-                if (c < D4) {
+                if (v < full_v || c < D4) {
                     const float4 q = *reinterpret_cast<const float4*>(us + h * D + 4 * c);
-                    dot[h] += dot4(k[0][v], q);
-                    dot[HG + h] += dot4(k[1][v], q);
+                    dot[h] = dot4acc(dot[h], k[0][v], q);
+                    dot[HG + h] = dot4acc(dot[HG + h], k[1][v], q);
                 }
             }
         warp_reduce8(dot, lane);
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
                         }
                         const float e = __expf(sv - m[h]);
                         s[h] += e;
-                        const float w = (p_drop > 0.f) ? e * kp[h * L + lrow[r]] : e;
+                        const float w = DROPOUT ? e * kp[h * L + lrow[r]] : e;
 #pragma unroll
                         for (int v = 0; v < NV; ++v) fma4(acc[h][v], w, k[r][v]);
                     }
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_fwd_kernel(
         float tot = 0.f;
         for (int ll = lane; ll < L; ll += 32) {
             float p = __expf(sc[h * L + ll] - M) * invS;
-            const bool keep = (p_drop > 0.f) ? (kp[h * L + ll] != 0.f) : true;
+            const bool keep = DROPOUT ? (kp[h * L + ll] != 0.f) : true;
             float pt = keep ? p * inv_keep : 0.f;
             attn[((int64_t)(h0 + h) * B + b) * L + ll] = pt;
             tot += pt;
@@ -342,12 +351,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_bwd_kernel(
             const int l = warp + j * AT_WARPS;
             ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
         }
-        int j0 = 0;
-        for (int l = warp; l < Lb; l += 2 * AT_WARPS, j0 += 2) {
+        int s0 = 0;                                      // ring slot of the pair's first row: 0, 2, 4, 0, ...
+        const int full_v = D4 >> 5;
+        for (int l = warp; l < Lb; l += 2 * AT_WARPS) {
+            const int sp = (s0 >= 2) ? s0 - 2 : s0 + RING - 2;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int lp = l + (RING - 2 + r) * AT_WARPS;
-                ring_issue<NV>(myring + ((j0 + RING - 2 + r) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+                ring_issue<NV>(myring + (sp + r) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
             }
             cp_async_wait<RING - 2>();
             __syncwarp();
@@ -356,12 +367,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_bwd_kernel(
             float4 k[2][NV];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                if (live[r]) ring_read<NV>(myring + ((j0 + r) % RING) * D, D4, lane, k[r]);
+                if (live[r]) ring_read<NV>(myring + (s0 + r) * D, D4, lane, k[r]);
                 else {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) k[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            s0 = (s0 == RING - 2) ? 0 : s0 + 2;
             float ds_[8], dt_[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ds_[i] = 0.f; dt_[i] = 0.f; }
@@ -370,13 +382,13 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_bwd_kernel(
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const int c = lane + 32 * v;
-                    if (c < D4) {
+                    if (v < full_v || c < D4) {
                         const float4 q = *reinterpret_cast<const float4*>(us + h * D + 4 * c);
                         const float4 g = *reinterpret_cast<const float4*>(gs + h * D + 4 * c);
-                        ds_[h] += dot4(k[0][v], q);
-                        ds_[HG + h] += dot4(k[1][v], q);
-                        dt_[h] += dot4(k[0][v], g);
-                        dt_[HG + h] += dot4(k[1][v], g);
+                        ds_[h] = dot4acc(ds_[h], k[0][v], q);
+                        ds_[HG + h] = dot4acc(ds_[HG + h], k[1][v], q);
+                        dt_[h] = dot4acc(dt_[h], k[0][v], g);
+                        dt_[HG + h] = dot4acc(dt_[HG + h], k[1][v], g);
                     }
                 }
             warp_reduce8(ds_, lane);
@@ -441,15 +453,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_q1_bwd_kernel(
             const int l = warp + j * AT_WARPS;
             ring_issue<NV>(myring + (j % RING) * D, bk + (int64_t)l * D, D4, lane, row_live(l));
         }
-        j0 = 0;
-        for (int l = warp; l < L; l += AT_WARPS, ++j0) {
+        s0 = 0;                                          // ring slot of the current row
+        for (int l = warp; l < L; l += AT_WARPS) {
             const int lp = l + (RING - 1) * AT_WARPS;
-            ring_issue<NV>(myring + ((j0 + RING - 1) % RING) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
+            ring_issue<NV>(myring + (s0 == 0 ? RING - 1 : s0 - 1) * D, bk + (int64_t)lp * D, D4, lane, row_live(lp));
             cp_async_wait<RING - 1>();
             __syncwarp();
             const bool live = row_live(l);
             float4 k[NV], dk[NV];
-            if (live) ring_read<NV>(myring + (j0 % RING) * D, D4, lane, k);
+            if (live) ring_read<NV>(myring + s0 * D, D4, lane, k);
+            s0 = (s0 == RING - 1) ? 0 : s0 + 1;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const int c = lane + 32 * v;
@@ -532,12 +545,27 @@ extern "C" int mgnns_attn_q1_fwd(const float* u, const float* bank, const float*
     cudaStream_t st = as_stream(stream);
     dim3 grid(B, (H + HG - 1) / HG);
     const int nv = (D / 4 + 31) / 32;
+#define AT_FWD(NVVAL, M, DR)                                                                                              \
+    do {                                                                                                                   \
+        cudaFuncSetAttribute(attn_q1_fwd_kernel<NVVAL, M, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        attn_q1_fwd_kernel<NVVAL, M, DR><<<grid, AT_THREADS, smem, st>>>(u, bank, mask, B, H, L, D, scale, p_drop, seed,   \
+                                                                         seed_offset, ctx, attn, psum, lse);              \
+    } while (0)
+#define AT_FWD_FLAGS(NVVAL)                                    \
+    do {                                                       \
+        if (mask != nullptr && p_drop > 0.f) AT_FWD(NVVAL, true, true);       \
+        else if (mask != nullptr) AT_FWD(NVVAL, true, false);  \
+        else if (p_drop > 0.f) AT_FWD(NVVAL, false, true);     \
+        else AT_FWD(NVVAL, false, false);                      \
+    } while (0)
     switch (nv) {
-        case 1: AT_DISPATCH(1, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
-        case 2: AT_DISPATCH(2, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
-        case 3: AT_DISPATCH(3, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
-        default: AT_DISPATCH(4, attn_q1_fwd_kernel, smem, grid, u, bank, mask, B, H, L, D, scale, p_drop, seed, seed_offset, ctx, attn, psum, lse); break;
+        case 1: AT_FWD_FLAGS(1); break;
+        case 2: AT_FWD_FLAGS(2); break;
+        case 3: AT_FWD_FLAGS(3); break;
+        default: AT_FWD_FLAGS(4); break;
     }
+#undef AT_FWD_FLAGS
+#undef AT_FWD
     MG_LAUNCH_CHECK("attn_q1_fwd");
     return 0;
 }
