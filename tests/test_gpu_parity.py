@@ -815,6 +815,72 @@ def test_cfg5_shaped_model_16_heads_large_label_graphs_vs_oracle(dev):
             np.testing.assert_allclose(params[n].grad.norm().item(), P[n].grad.norm().item(), rtol=5e-3, err_msg=n)
 
 
+def test_graphed_train_step_matches_eager_steps(dev, ops):
+    """GraphedTrainStep (whole step captured as one CUDA graph: four-stream forward/backward, deferred weight
+    gradients, clip, fused Adam) against the same three steps run eagerly on one stream — eval mode, so no dropout
+    randomness; parameters must agree to summation-order noise.  Also exercises update_lengths() on a second batch."""
+    from mgnns_b200.graph_step import GraphedTrainStep
+    cfg = dict(H.MODEL_CFG, B=16, V=300, seed=51)
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=51, docs=500)
+    batches = []
+    for sd in (51, 52):
+        c = dict(cfg, seed=sd)
+        text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(c)
+        batches.append(dict(text=text.to(dev), lens=lens, mask=mask.to(dev), fo=fo.to(dev), fp=fp.to(dev),
+                            oinp=oinp.to(dev), pinp=pinp.to(dev), labels=labels.to(dev)))
+    crit = torch.nn.CrossEntropyLoss()
+
+    def fresh():
+        m = build_model(dev, cfg, emap, count).eval()
+        # a large eps keeps Adam's normalised update proportional to the gradient for near-zero gradients, so that
+        # summation-order noise (fp32 atomics) cannot flip an update of size lr
+        o = torch.optim.Adam(m.get_config_optim(1e-3, 0.1), lr=1e-3, weight_decay=1e-5, eps=1e-2, capturable=True,
+                             fused=True)
+        return m, o
+
+    # eager reference: batch 0, batch 1, batch 0
+    m_e, o_e = fresh()
+    losses_e = []
+    for b in (batches[0], batches[1], batches[0]):
+        o_e.zero_grad(set_to_none=True)
+        loss = crit(m_e(b['text'], b['lens'], b['mask'], b['fo'], b['fp'], b['oinp'], b['pinp']), b['labels'])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m_e.parameters(), 10.0)
+        o_e.step()
+        losses_e.append(loss.item())
+
+    # graph: static buffers start as batch 0; warm-up steps inside the constructor would move the parameters, so the
+    # model/optimizer state is restored after capture
+    m_g, o_g = fresh()
+    m_g.branch_streams = True
+    static = {k: (v.clone() if torch.is_tensor(v) and k != 'lens' else v) for k, v in batches[0].items()}
+    p0 = {n: p.detach().clone() for n, p in m_g.named_parameters()}
+    g = GraphedTrainStep(m_g, o_g, crit, static, clip_norm=10.0, world_size=1, warmup=1, plan_capacity=16 * 100)
+    with torch.no_grad():
+        for n, p in m_g.named_parameters():
+            p.copy_(p0[n])
+    for st in o_g.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                v.zero_()
+    losses_g = []
+    for b in (batches[0], batches[1], batches[0]):
+        for k in ('text', 'mask', 'fo', 'fp', 'labels'):
+            static[k].copy_(b[k])
+        g.update_lengths(b['lens'])
+        losses_g.append(g.replay().item())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(losses_g, losses_e, rtol=2e-4)
+    pe = dict(m_e.named_parameters())
+    worst = 0.0
+    for n, p in m_g.named_parameters():
+        d = (p.detach() - pe[n].detach()).abs().max().item()
+        worst = max(worst, d)
+        assert d < 2e-5, (n, d)
+    moved = max((p.detach() - p0[n]).abs().max().item() for n, p in m_g.named_parameters())
+    assert moved > 1e-4, "the captured step did not update the parameters"
+
+
 def test_train_mode_step_is_finite_and_deterministic(dev):
     cfg = dict(H.MODEL_CFG, B=8, V=300, seed=31)
     emap, count = synth.synthetic_edge_map(cfg['V'], seed=31, docs=500)
