@@ -863,6 +863,13 @@ def test_graphed_train_step_matches_eager_steps(dev, ops):
         for k, v in st.items():
             if torch.is_tensor(v):
                 v.zero_()
+    # Like the reference engine (optimizer.zero_grad(), engine:841), the step only clears the gradients of the
+    # parameters the optimizer owns: the never-stepped ones (classifier tail, image-bank Linears, ... SURVEY §0.4)
+    # keep ACCUMULATING across steps and count toward the clip norm.  The warm-up step left one such contribution in
+    # the graph's static .grad buffers; clear it so that both runs start from the same state.
+    for p in m_g.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
     losses_g = []
     for b in (batches[0], batches[1], batches[0]):
         for k in ('text', 'mask', 'fo', 'fp', 'labels'):
