@@ -36,7 +36,7 @@ WORKLOAD = ("cfg4 MGNNS head training step: TumEmo-shaped synthetic batch, %d sa
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=512, help='samples per GPU')
@@ -114,7 +114,7 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
