@@ -1,4 +1,4 @@
-"""SpMM-only timing on the cfg-2 word graph: python scripts/spmm_bench.py [B] [hot_cols] (env MGNNS_SPMM_VARIANT)."""
+"""SpMM-only timing on the cfg-2 word graph (CUDA events): python scripts/spmm_bench.py [B]."""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,6 @@ from mgnns_b200.api.graph_util import CSRAdjacency
 
 dev = torch.device('cuda', 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-hot = int(sys.argv[2]) if len(sys.argv) > 2 else 160
 N, F = 10000, 300
 rowptr, cols, val = synth.cfg2_word_graph(N, seed=0)
 csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, dev)
@@ -31,5 +30,5 @@ with torch.no_grad():
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 nnz = cols.shape[0]
-print("variant=%s hot=%d B=%d: %.3f ms  gather %.1f TB/s  hbm-algorithmic %.0f GB/s  max|err| %.1e"
-      % (os.environ.get('MGNNS_SPMM_VARIANT', '0'), hot, B, ms, nnz * B * F * 4 / ms / 1e9, 8.0 * B * N * F / ms / 1e6, err))
+print("B=%d: %.3f ms  gather %.1f TB/s  hbm-algorithmic %.0f GB/s  max|err| %.1e"
+      % (B, ms, nnz * B * F * 4 / ms / 1e9, 8.0 * B * N * F / ms / 1e6, err))
