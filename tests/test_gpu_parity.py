@@ -888,6 +888,37 @@ def test_graphed_train_step_matches_eager_steps(dev, ops):
     assert moved > 1e-4, "the captured step did not update the parameters"
 
 
+@pytest.mark.parametrize("num_labels", [7, 3])
+def test_cfg3_full_size_inference_batch_independence(dev, num_labels):
+    """BASELINE cfg 3 (inference, batch 1024, TumEmo 7 / MVSA 3 classes) at full size through size-independent
+    properties: every sample's logits are independent of what else is in the batch (the first 32 samples alone, and a
+    permuted batch, give the same rows), and a 32-sample slice matches the CPU oracle."""
+    B = 1024
+    cfg = dict(H.MODEL_CFG, B=B, V=2000, seed=61 + num_labels, num_labels=num_labels)
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=61, docs=3000)
+    model = build_model(dev, cfg, emap, count).eval()
+    model.branch_streams = True
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    dt = lambda t: t.to(dev)          # noqa: E731
+    with torch.no_grad():
+        full = model(dt(text), lens, dt(mask), dt(fo), dt(fp), dt(oinp), dt(pinp))
+        head = model(dt(text[:32]), lens[:32], dt(mask[:32]), dt(fo[:32]), dt(fp[:32]), dt(oinp[:32]), dt(pinp[:32]))
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+        shuf = model(dt(text[perm]), lens[perm], dt(mask[perm]), dt(fo[perm]), dt(fp[perm]), dt(oinp[perm]), dt(pinp[perm]))
+    assert full.shape == (B, num_labels) and torch.isfinite(full).all()
+    # the image-bank tiles straddle sample boundaries and the LSTM tiles depend on the length order: fp32 rounding only
+    close(full[:32], head, 1e-4, 1e-5)
+    close(shuf, full[perm.to(dev)], 1e-4, 1e-5)
+    assert torch.equal(shuf.argmax(1), full[perm.to(dev)].argmax(1))
+    P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    query = torch.from_numpy(synth.label_graphs()['label_glove'])[:num_labels]
+    with torch.no_grad():
+        ref = O.model_forward(P, text[:32], lens[:32], mask[:32], fo[:32], fp[:32], oinp[0], pinp[0], query,
+                              lambda u, v: emap[u, v], cfg)
+    close(full[:32], ref, 1e-3, 1e-4)
+    assert torch.equal(full[:32].argmax(1).cpu(), ref.argmax(1))
+
+
 def test_train_mode_step_is_finite_and_deterministic(dev):
     cfg = dict(H.MODEL_CFG, B=8, V=300, seed=31)
     emap, count = synth.synthetic_edge_map(cfg['V'], seed=31, docs=500)
