@@ -194,6 +194,31 @@ int mgnns_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, in
                     const float* bias, int act, float slope, int M, int N, int K, int precision,
                     float* workspace, int64_t workspace_floats, float* C, int64_t ldc, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused graph-convolution layer for batched node features, one kernel:
+ *   Y[b] = act((A_hat . X[b]) . W + bias)      X [batch, n_cols, K] (row stride K), Y [batch, n_rows, N] (row stride ldy)
+ * The aggregated rows A_hat.X[b] are gathered straight into the shared-memory operand of the tcgen05 tensor core
+ * (they never exist in HBM); W [K,N] is streamed by TMA.  A_hat comes as a host-built execution plan of the CSR
+ * matrix (mgnns_b200.api.graph_util.CSRAdjacency.fused_plan): 128-row tiles dealt by degree rank, each row cut
+ * into segments of at most 128 edges.
+ *   tile_seg_ptr   int32 [n_tiles + 1]     segment range of a tile
+ *   segs           int32 [n_segs, 4]       {first edge, edges (<= 128), row in tile, 1 = the row's only segment}
+ *   edges          int32 [nnz, 2]          {byte offset of the neighbour row inside X[b] (= col * K * 4), bits of val}
+ *   tile_rows      int32 [n_tiles * 128]   output row of each tile slot, -1 = padding
+ *   tile_multi_ptr int32 [n_tiles + 1], multi_rows int32 [...]   tile slots whose row spans several segments
+ *   precision: 0 = TF32 operands, 1 = 3xTF32 split (fp32-class); workspace: mgnns_gcn_fused_workspace() floats
+ *   constraints: K % 4 == 0, N % 32 == 0, N <= 512, X 16-byte aligned, strideX % 4 == 0
+ * ref: GraphConvolution.forward, models/Multi_GCN_Multihead_att.py:52-58 (+ the caller's activation, :470-472);
+ *      BASELINE.json configs[1] (10k-node word graph, 300 -> 512, batch 256)
+ * ------------------------------------------------------------------------- */
+int64_t mgnns_gcn_fused_workspace(int N, int K, int precision);
+int mgnns_gcn_fused_tc(const float* X, int64_t strideX, int batch,
+                       const int32_t* tile_seg_ptr, const int32_t* segs, const int32_t* edges,
+                       const int32_t* tile_rows, const int32_t* tile_multi_ptr, const int32_t* multi_rows,
+                       int n_tiles, const float* W, int64_t ldw, const float* bias, int act, float slope,
+                       int K, int N, int precision, float* workspace, int64_t workspace_floats,
+                       float* Y, int64_t ldy, int64_t strideY, void* stream);
+
 /* Weight-gradient product on the tensor cores:  C[M,N] = A[K,M]^T . B[K,N]  with a long reduction (K = rows of
  * a batch / tokens).  A and B are row-major with the reduction index as the row (lda, ldb multiples of 4, 16-byte
  * aligned); C is overwritten.  K slices are accumulated with fp32 atomics (summation order varies run to run).

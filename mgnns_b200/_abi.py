@@ -54,6 +54,9 @@ SIGNATURES = {
     "mgnns_linear_tc_workspace": (c_int64, [c_int, c_int, c_int64, c_int, c_int]),
     "mgnns_linear_tc": (c_int, [P, c_int64, P, c_int64, c_int, P, c_int, c_float, c_int, c_int, c_int, c_int,
                                 P, c_int64, P, c_int64, P]),
+    "mgnns_gcn_fused_workspace": (c_int64, [c_int, c_int, c_int]),
+    "mgnns_gcn_fused_tc": (c_int, [P, c_int64, c_int, P, P, P, P, P, P, c_int, P, c_int64, P, c_int, c_float,
+                                   c_int, c_int, c_int, P, c_int64, P, c_int64, c_int64, P]),
     "mgnns_wgrad_tc": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, c_int64, P]),
     "mgnns_lstm_prep_whh": (c_int, [P, P, c_int, P]),
     "mgnns_lstm_rec_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P, P, P, P]),

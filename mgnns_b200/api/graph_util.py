@@ -86,6 +86,86 @@ class CSRAdjacency:
         return torch.ops.mgnns.spmm_csr(self.rowptr, self.col, self.val, x,
                                         self.t_rowptr, self.t_col, self.t_val, self.n_rows)
 
+    def fused_plan(self, ldx: int) -> "FusedGcnPlan":
+        """Execution plan of this matrix for the fused layer kernel (mgnns_gcn_fused_tc), for node features whose
+        rows are `ldx` floats apart.  Built once on the host and cached."""
+        plans = self.__dict__.setdefault('_fused_plans', {})
+        plan = plans.get(ldx)
+        if plan is None:
+            plan = plans[ldx] = FusedGcnPlan.build(self.rowptr.cpu().numpy(), self.col.cpu().numpy(),
+                                                   self.val.cpu().numpy(), ldx, self.rowptr.device)
+        return plan
+
+
+FUSED_TILE_ROWS = 128
+FUSED_SEG_EDGES = 128
+
+
+def fused_plan_arrays(rowptr, col, val, ldx, tile_rows=FUSED_TILE_ROWS, seg_edges=FUSED_SEG_EDGES):
+    """Host arrays of the fused-layer plan (see include/mgnns_b200.h, mgnns_gcn_fused_tc).
+
+    Rows are ranked by degree (descending, stable) and dealt to the T = ceil(n/128) tiles round-robin — tile t holds
+    the rows ranked t, t+T, t+2T, ... in slots 0, 1, 2, ... — so every tile carries the same share of the edges.
+    Each row becomes ceil(degree/128) segments (at least one, so empty rows still zero their slot); a tile's
+    segments are sorted by length (descending) because the kernel deals them to its gather warps round-robin."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int64)
+    val = np.ascontiguousarray(np.asarray(val, dtype=np.float32))
+    n = rowptr.shape[0] - 1
+    if int(col.max(initial=0)) * ldx * 4 >= 2 ** 32:
+        raise ValueError("fused GCN plan: neighbour-row byte offsets do not fit 32 bits")
+    deg = np.diff(rowptr)
+    n_tiles = max(1, (n + tile_rows - 1) // tile_rows)
+    order = np.argsort(-deg, kind='stable')
+    rank = np.arange(n)
+    tile_of, slot_of = rank % n_tiles, rank // n_tiles
+    rows_tbl = np.full(n_tiles * tile_rows, -1, dtype=np.int32)
+    rows_tbl[tile_of * tile_rows + slot_of] = order
+    # one descriptor per (tile, slot), padding slots included (they must be zeroed too)
+    slot_row = rows_tbl.astype(np.int64)
+    slot_deg = np.where(slot_row >= 0, deg[np.maximum(slot_row, 0)], 0)
+    slot_beg = np.where(slot_row >= 0, rowptr[np.maximum(slot_row, 0)], 0)
+    n_seg = np.maximum(1, (slot_deg + seg_edges - 1) // seg_edges)
+    total = int(n_seg.sum())
+    owner = np.repeat(np.arange(n_tiles * tile_rows), n_seg)              # slot index of every segment
+    first = np.cumsum(n_seg) - n_seg
+    j = np.arange(total) - np.repeat(first, n_seg)                        # index of the segment within its row
+    seg_beg = slot_beg[owner] + j * seg_edges
+    seg_len = np.minimum(seg_edges, slot_deg[owner] - j * seg_edges).clip(min=0)
+    seg_tile = owner // tile_rows
+    key = np.lexsort((-seg_len, seg_tile))                                # by tile, longest first
+    segs = np.stack([seg_beg[key], seg_len[key], (owner % tile_rows)[key], (n_seg[owner] == 1)[key].astype(np.int64)],
+                    axis=1).astype(np.int32)
+    tile_seg_ptr = np.zeros(n_tiles + 1, dtype=np.int64)
+    np.add.at(tile_seg_ptr, seg_tile + 1, 1)
+    tile_seg_ptr = np.cumsum(tile_seg_ptr).astype(np.int32)
+    multi_slot = np.nonzero(n_seg > 1)[0]
+    tile_multi_ptr = np.zeros(n_tiles + 1, dtype=np.int64)
+    np.add.at(tile_multi_ptr, multi_slot // tile_rows + 1, 1)
+    tile_multi_ptr = np.cumsum(tile_multi_ptr).astype(np.int32)
+    multi_rows = (multi_slot % tile_rows).astype(np.int32)
+    edges = np.empty((col.shape[0], 2), dtype=np.int32)
+    edges[:, 0] = (col * ldx * 4).astype(np.uint32).view(np.int32)
+    edges[:, 1] = val.view(np.int32)
+    return dict(tile_seg_ptr=tile_seg_ptr, segs=np.ascontiguousarray(segs), edges=edges, tile_rows=rows_tbl,
+                tile_multi_ptr=tile_multi_ptr, multi_rows=multi_rows, n_tiles=n_tiles, n_rows=n)
+
+
+class FusedGcnPlan:
+    """Device copy of fused_plan_arrays()."""
+
+    def __init__(self, arrays, ldx, device):
+        self.ldx, self.n_tiles, self.n_rows = ldx, arrays['n_tiles'], arrays['n_rows']
+        for k in ('tile_seg_ptr', 'segs', 'edges', 'tile_rows', 'tile_multi_ptr', 'multi_rows'):
+            a = arrays[k]
+            if a.size == 0:
+                a = np.zeros((1,) + a.shape[1:], dtype=np.int32)            # keep a valid pointer
+            setattr(self, k, torch.from_numpy(np.ascontiguousarray(a)).to(device))
+
+    @classmethod
+    def build(cls, rowptr, col, val, ldx, device):
+        return cls(fused_plan_arrays(rowptr, col, val, ldx), ldx, device)
+
 
 _CSR_CACHE = {}
 

@@ -1,6 +1,6 @@
 """MGNNS model assembly with the reference's constructors, forward signature and state_dict names
 (ref: models/Multi_GCN_Multihead_att.py).  All arithmetic named by the north star runs in the mgnns
-ops; the ResNet trunks (torchvision/cuDNN) and the packed bi-LSTM (cuDNN) stay torch modules.
+ops (the bi-LSTM included: ops.packed_bilstm); only the ResNet trunks (torchvision/cuDNN) stay torch modules.
 """
 import math
 import os
@@ -69,6 +69,11 @@ class GraphConvolution(nn.Module):
     def forward(self, input, adj, act=ops.ACT_NONE, slope=0.0):
         csr = as_csr(adj)
         bias = None if self.bias is None else self.bias.view(-1)
+        needs_grad = torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)
+        if (not needs_grad and input.dim() == 3 and input.shape[0] * csr.n_rows >= 2048
+                and csr.n_rows == csr.n_cols == input.shape[1] and ops.gcn_fused_ok(input, self.weight)):
+            # batched node features, forward only: one kernel, the aggregated rows never reach HBM
+            return ops.gcn_fused(csr.fused_plan(input.shape[2]), input, self.weight, bias, act, slope)
         if self.in_features <= self.out_features:
             return ops.matmul_nn(csr.spmm(input), self.weight, bias, act, slope)
         out = csr.spmm(ops.matmul_nn(input, self.weight))

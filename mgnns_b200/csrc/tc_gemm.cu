@@ -410,18 +410,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
-// ring of work counters for the dynamic tile scheduler (tc_common.cuh)
-__device__ int g_tile_counters[256];
+// Work counters for the dynamic tile scheduler (tc_common.cuh).  Eager launches cycle through a 256-slot ring;
+// launches that are being captured into a CUDA graph get a slot of their own from a second pool that eager
+// launches never touch (the slot address is baked into the graph and re-zeroed by the captured memset node on
+// every replay), so a replaying graph and an eager kernel on another stream cannot share a counter.  Symbol
+// addresses are per device, so the base pointers are looked up per device.
+constexpr unsigned EAGER_SLOTS = 256, GRAPH_SLOTS = 4096;
+__device__ int g_tile_counters[EAGER_SLOTS];
+__device__ int g_graph_counters[GRAPH_SLOTS];
 
 int* next_tile_counter(cudaStream_t st) {
-    static int* base = nullptr;
-    static std::atomic<unsigned> next{0};
-    if (!base) {
-        void* ptr = nullptr;
-        if (cudaGetSymbolAddress(&ptr, g_tile_counters) != cudaSuccess) return nullptr;
-        base = static_cast<int*>(ptr);
+    constexpr int MAX_DEV = 64;
+    static std::atomic<int*> eager_base[MAX_DEV];
+    static std::atomic<int*> graph_base[MAX_DEV];
+    static std::atomic<unsigned> next_eager{0}, next_graph{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    int* eb = eager_base[dev].load(std::memory_order_acquire);
+    if (!eb) {
+        void *pe = nullptr, *pg = nullptr;
+        if (cudaGetSymbolAddress(&pe, g_tile_counters) != cudaSuccess) return nullptr;
+        if (cudaGetSymbolAddress(&pg, g_graph_counters) != cudaSuccess) return nullptr;
+        graph_base[dev].store(static_cast<int*>(pg), std::memory_order_release);
+        eager_base[dev].store(static_cast<int*>(pe), std::memory_order_release);
+        eb = static_cast<int*>(pe);
     }
-    int* c = base + (next.fetch_add(1, std::memory_order_relaxed) % 256u);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return nullptr;
+    int* c;
+    if (cap == cudaStreamCaptureStatusActive)
+        c = graph_base[dev].load(std::memory_order_acquire) + (next_graph.fetch_add(1, std::memory_order_relaxed) % GRAPH_SLOTS);
+    else
+        c = eb + (next_eager.fetch_add(1, std::memory_order_relaxed) % EAGER_SLOTS);
     if (cudaMemsetAsync(c, 0, sizeof(int), st) != cudaSuccess) return nullptr;
     return c;
 }

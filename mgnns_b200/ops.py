@@ -505,6 +505,73 @@ def _spmm_backward(ctx, g):
 torch.library.register_autograd("mgnns::spmm_csr", _spmm_backward, setup_context=_spmm_setup)
 
 
+# ----------------------------------------------------------------------------- fused graph-convolution layer
+_LIB.define("gcn_fused(Tensor x, Tensor weight, Tensor? bias, Tensor tile_seg_ptr, Tensor segs, Tensor edges, "
+            "Tensor tile_rows, Tensor tile_multi_ptr, Tensor multi_rows, int n_tiles, int n_rows, int act, "
+            "float slope) -> Tensor")
+_gcn_fused = _lib.mgnns_gcn_fused_tc
+_gcn_fused_ws = _lib.mgnns_gcn_fused_workspace
+
+
+def gcn_fused_ok(x, weight) -> bool:
+    """Shapes / mode the fused layer kernel covers (forward only; callers that need gradients use spmm + mm)."""
+    K, N = weight.shape
+    return (_PRECISIONS[_precision] is not None and x.dim() == 3 and x.is_cuda and x.dtype is _f32
+            and K % 4 == 0 and N % 32 == 0 and N <= 512 and K <= N and x.shape[2] == K
+            and os.environ.get("MGNNS_GCN_FUSED", "1") != "0")
+
+
+def _gcn_fused_impl(x, weight, bias, tile_seg_ptr, segs, edges, tile_rows, tile_multi_ptr, multi_rows, n_tiles, n_rows,
+                    act, slope):
+    _need_cuda(x, weight, bias, tile_seg_ptr, segs, edges, tile_rows, tile_multi_ptr, multi_rows)
+    prec = _PRECISIONS[_precision]
+    if prec is None:
+        raise RuntimeError("mgnns::gcn_fused runs on the tensor cores (precision tf32x3 or tf32), not in fp32 mode")
+    if x.dim() != 3:
+        raise RuntimeError("mgnns::gcn_fused: x must be [batch, nodes, in_features]")
+    x = _f32c(x, "x")
+    weight = _f32c(weight, "weight")
+    batch, _, K = x.shape
+    if weight.shape[0] != K:
+        raise RuntimeError("mgnns::gcn_fused: weight has %d rows, x has %d features" % (weight.shape[0], K))
+    N = weight.shape[1]
+    for t in (tile_seg_ptr, segs, edges, tile_rows, tile_multi_ptr, multi_rows):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise RuntimeError("mgnns::gcn_fused: plan arrays must be contiguous int32")
+    bp = None
+    if bias is not None:
+        bias = _f32c(bias.reshape(-1), "bias")
+        if bias.numel() != N:
+            raise RuntimeError("mgnns::gcn_fused: bias has %d elements, expected %d" % (bias.numel(), N))
+        bp = bias.data_ptr()
+    y = torch.empty((batch, n_rows, N), device=x.device, dtype=_f32)
+    wsf = int(_gcn_fused_ws(N, K, prec))
+    ws = torch.empty((max(wsf, 4),), device=x.device, dtype=_f32)
+    with _timed("gcn_fused"):
+        rc = _gcn_fused(x.data_ptr(), x.stride(0), batch, tile_seg_ptr.data_ptr(), segs.data_ptr(), edges.data_ptr(),
+                        tile_rows.data_ptr(), tile_multi_ptr.data_ptr(), multi_rows.data_ptr(), n_tiles,
+                        weight.data_ptr(), weight.stride(0), bp, act, slope, K, N, prec, ws.data_ptr(), wsf,
+                        y.data_ptr(), N, n_rows * N, _raw_stream(x.device.index))
+    if rc:
+        _check(rc, "gcn_fused")
+    return y
+
+
+def _gcn_fused_fake(x, weight, bias, tile_seg_ptr, segs, edges, tile_rows, tile_multi_ptr, multi_rows, n_tiles, n_rows,
+                    act, slope):
+    return x.new_empty((x.shape[0], n_rows, weight.shape[1]))
+
+
+_LIB.impl("gcn_fused", _gcn_fused_impl, "CUDA")
+torch.library.register_fake("mgnns::gcn_fused", _gcn_fused_fake)
+
+
+def gcn_fused(plan, x, weight, bias=None, act=ACT_NONE, slope=0.0):
+    """act((Â·x)·weight + bias) in one kernel; `plan` = CSRAdjacency.fused_plan(x.shape[2])."""
+    return torch.ops.mgnns.gcn_fused(x, weight, bias, plan.tile_seg_ptr, plan.segs, plan.edges, plan.tile_rows,
+                                     plan.tile_multi_ptr, plan.multi_rows, plan.n_tiles, plan.n_rows, act, float(slope))
+
+
 # ----------------------------------------------------------------------------- dense -> CSR
 def dense_to_csr(adj: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """[n,m] fp32 CUDA matrix -> (rowptr int32[n+1], col int32[nnz], val fp32[nnz]); one host sync for nnz."""

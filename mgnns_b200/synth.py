@@ -145,20 +145,41 @@ def fill_parameters(module_or_dict, seed=0, scale=None):
 
 
 def cfg2_word_graph(N=10000, mean_degree=64, seed=0):
-    """SURVEY §8d cfg 2 adjacency: PMI-like word graph in CSR — power-law out-degrees (mean ~`mean_degree`
-    draws + a self loop, duplicates merged), neighbours drawn from a heavy-tailed popularity law, rows
-    normalised to sum 1.  Returns host arrays (rowptr int64 [N+1], col int64 [nnz], val float32 [nnz])."""
+    """SURVEY §8d cfg 2 adjacency: PMI-like word graph in CSR — power-law row degrees (exactly
+    `mean_degree`·N distinct off-diagonal neighbours in total, each row's drawn WITHOUT replacement from a
+    heavy-tailed popularity law by the Gumbel top-k trick) plus a self loop on every row, so
+    nnz = (mean_degree + 1)·N (650,000 at the defaults); rows normalised to sum 1.
+    Returns host arrays (rowptr int64 [N+1], col int64 [nnz] sorted within a row, val float32 [nnz])."""
     rs = np.random.RandomState(seed)
-    deg = np.clip((rs.pareto(1.3, N) + 1) * 20, 1, 3000).astype(np.int64)
-    deg = np.maximum(1, (deg * (float(mean_degree) * N / deg.sum())).astype(np.int64))
+    raw = np.clip((rs.pareto(1.3, N) + 1) * 20, 1, min(3000, N - 1))
+    deg = np.maximum(1, np.floor(raw * (float(mean_degree) * N / raw.sum()))).astype(np.int64)
+    deg = np.minimum(deg, min(3000, N - 1))
+    # fix the total to mean_degree*N exactly (largest rows absorb the rounding remainder)
+    order = np.argsort(-raw, kind='stable')
+    rem, k = int(mean_degree) * N - int(deg.sum()), 0
+    while rem != 0:
+        i = order[k % N]
+        step = 1 if rem > 0 else -1
+        if 1 <= deg[i] + step <= min(3000, N - 1):
+            deg[i] += step
+            rem -= step
+        k += 1
     pop = (rs.pareto(1.1, N) + 1)
-    pop /= pop.sum()
-    rows, cols = [], []
-    for i in range(N):
-        c = np.unique(np.concatenate([rs.choice(N, deg[i], p=pop), [i]]))
-        rows.append(np.full(c.shape, i))
-        cols.append(c)
-    rows, cols = np.concatenate(rows), np.concatenate(cols)
-    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=N))])
-    val = (1.0 / np.diff(rowptr))[rows].astype(np.float32)
+    logp = np.log(pop / pop.sum())
+    cols = []
+    for r0 in range(0, N, 500):
+        r1 = min(N, r0 + 500)
+        key = logp[None, :] + rs.gumbel(size=(r1 - r0, N))
+        key[np.arange(r1 - r0), np.arange(r0, r1)] = -np.inf          # the self loop is added explicitly
+        kmax = int(deg[r0:r1].max())
+        top = np.argpartition(-key, kmax - 1, axis=1)[:, :kmax]
+        topk = np.take_along_axis(key, top, axis=1)
+        srt = np.argsort(-topk, axis=1)
+        top = np.take_along_axis(top, srt, axis=1)
+        for i in range(r0, r1):
+            cols.append(np.sort(np.concatenate([top[i - r0, :deg[i]], [i]])))
+    rowptr = np.concatenate([[0], np.cumsum(deg + 1)]).astype(np.int64)
+    cols = np.concatenate(cols).astype(np.int64)
+    rows = np.repeat(np.arange(N), deg + 1)
+    val = (1.0 / (deg + 1))[rows].astype(np.float32)
     return rowptr, cols, val

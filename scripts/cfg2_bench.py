@@ -1,6 +1,7 @@
-"""cfg 2 microbench driver: GraphConvolution(300->512)+ReLU on the 10k-node word graph, batch 256.
-Prints per-kernel CUDA-event times for each precision mode and hot-column setting; checks one sample against
-a float64 torch reference.  Usage: python scripts/cfg2_bench.py [B] [hot_cols ...]"""
+"""cfg 2 microbench driver: GraphConvolution(300->512)+ReLU on the 10k-node word graph (nnz 650,000).
+Times the fused kernel (gather -> smem operand -> tcgen05) and the two-kernel path (SpMM + tcgen05 dense layer) with
+CUDA events, per precision mode, and checks one sample against a float64 torch reference.
+Usage: python scripts/cfg2_bench.py [B] [iters]"""
 import os
 import sys
 
@@ -15,43 +16,43 @@ from mgnns_b200.api.multi_gcn import GraphConvolution
 
 dev = torch.device('cuda', 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-hots = [0]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 N, Fin, Fout = 10000, 300, 512
 rowptr, cols, val = synth.cfg2_word_graph(N, seed=0)
 nnz = cols.shape[0]
 torch.manual_seed(0)
 gc = GraphConvolution(Fin, Fout).to(dev)
 x = torch.randn(B, N, Fin, device=dev)
+csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, dev)
 
-# float64 reference for sample 0
 A = torch.zeros(N, N, dtype=torch.float64)
 rows = np.repeat(np.arange(N), np.diff(rowptr))
 A[torch.from_numpy(rows), torch.from_numpy(cols)] = torch.from_numpy(val).double()
-ref = torch.relu(A @ x[0].double().cpu() @ gc.weight.detach().double().cpu())
+ref = torch.relu(A @ x[B - 1].double().cpu() @ gc.weight.detach().double().cpu())
+alg_bytes = 4 * (B * N * Fin + B * N * Fout + Fin * Fout) + 8 * nnz + 4 * (N + 1)
+print("cfg2: N=%d nnz=%d B=%d  algorithmic bytes %.3f GB, gather bytes %.1f GB" % (N, nnz, B, alg_bytes / 1e9, 4.0 * nnz * B * Fin / 1e9), flush=True)
 
-for hot in hots:
-    csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, dev)
-    for mode in ('tf32x3', 'tf32', 'fp32'):
-        if mode == 'fp32' and B > 64:
-            continue
+for fused in ('1', '0'):
+    os.environ['MGNNS_GCN_FUSED'] = fused
+    for mode in ('tf32x3', 'tf32'):
         ops.set_precision(mode)
+        names = ['gcn_fused'] if fused == '1' else ['spmm_csr', 'linear_tc']
         with torch.no_grad():
             for _ in range(2):
                 y = gc(x, csr, ops.ACT_RELU)
-            err = (y[0].double().cpu() - ref).abs().max().item()
-            ops.KernelTimers.reset(['spmm_csr', 'linear_tc'])
+            err = (y[B - 1].double().cpu() - ref).abs().max().item()
+            ops.KernelTimers.reset(names)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(3):
+            for _ in range(iters):
                 y = gc(x, csr, ops.ACT_RELU)
             e1.record()
             torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
-        sp, _ = ops.KernelTimers.mean_ms('spmm_csr')
-        li, _ = ops.KernelTimers.mean_ms('linear_tc')
+        ms = e0.elapsed_time(e1) / iters
+        parts = "  ".join("%s %.3f ms" % (n, ops.KernelTimers.mean_ms(n)[0] or float('nan')) for n in names)
         ops.KernelTimers.reset([])
-        print("B=%d mode=%s: total %.3f ms  spmm %s ms  linear_tc %s ms  max|err| %.2e (ref rms %.3f)"
-              % (B, mode, ms, "%.3f" % sp if sp else "-", "%.3f" % li if li else "-", err, ref.pow(2).mean().sqrt().item()),
+        print("fused=%s mode=%s: total %.3f ms (%.0f GB/s algorithmic = %.3f of 6535.7)  %s  max|err| %.2e (ref rms %.3f)"
+              % (fused, mode, ms, alg_bytes / ms / 1e6, alg_bytes / ms / 1e6 / 6535.7, parts, err, ref.pow(2).mean().sqrt().item()),
               flush=True)
         del y

@@ -5,6 +5,7 @@ Tolerances (fp32 mode, stated per BASELINE.json north_star): logits 1e-3 relativ
 argmax identical, integer counts / edge ids bit-exact.  Kernel-level checks use tighter bounds.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -168,6 +169,102 @@ def test_graph_convolution_matches_reference_golden(dev, golden):
     x = torch.from_numpy(lg['object_glove']).float()
     ref = O.graph_convolution(x, adj.cpu(), gcs.weight.detach())
     close(gcs.to(dev)(x.to(dev), adj), ref, 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------- fused GCN layer
+def _csr_host(adj):
+    rows, cols = np.nonzero(adj.numpy())
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=adj.shape[0]))])
+    return rowptr, cols, adj.numpy()[rows, cols]
+
+
+@pytest.mark.parametrize("n,K,N,batch,bias,act", [
+    (300, 300, 512, 9, False, 1),       # cfg-2 feature sizes on a small graph, ragged last K chunk (300 = 9*32 + 12)
+    (130, 64, 256, 20, True, 2),        # single accumulator half, bias + LeakyReLU, two row tiles with padding slots
+    (1000, 128, 320, 3, True, 0),       # N1 = 64 second half, no activation
+    (97, 32, 32, 25, False, 1),         # one K chunk, smallest N
+])
+def test_gcn_fused_matches_float64(ops, dev, n, K, N, batch, bias, act):
+    """mgnns_gcn_fused_tc against relu((Â·X)·W + b) in float64: hub rows longer than one 128-edge segment (combined
+    through the shared-memory scratch tile), empty rows, rows of every tile slot."""
+    from mgnns_b200.api.graph_util import CSRAdjacency
+    from mgnns_b200.api.multi_gcn import GraphConvolution
+    adj = random_adj(n, n, 0.04, seed=n)
+    g = torch.Generator().manual_seed(n + 1)
+    adj[5] = torch.randn(n, generator=g)                 # a dense hub row: ceil(n/128) segments
+    adj[7, : min(n, 200)] = torch.randn(min(n, 200), generator=g)
+    adj[3] = 0                                           # an empty row
+    adj[:, 11] = torch.randn(n, generator=g)             # a hub column
+    adj[3] = 0
+    adj = adj / adj.abs().sum(1, keepdim=True).clamp(min=1.0)      # Â-like row scale: outputs stay O(1)
+    rowptr, cols, val = _csr_host(adj)
+    csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, n, dev)
+    gc = GraphConvolution(K, N, bias=bias)
+    synth.fill_parameters(gc, seed=K)
+    gc.to(dev)
+    x = rnd(batch, n, K, seed=N)
+    slope = 0.2
+    assert ops.gcn_fused_ok(x.to(dev), gc.weight)
+    l0 = ops._abi.launch_count()
+    with torch.no_grad():
+        y = gc(x.to(dev), csr, act, slope)
+    assert ops._abi.launch_count() - l0 == 2             # weight split + the fused kernel, nothing else
+    ref = adj.double() @ x.double() @ gc.weight.detach().cpu().double()
+    if bias:
+        ref = ref + gc.bias.detach().cpu().double().view(1, 1, -1)
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.leaky_relu(ref, slope)
+    close(y, ref, 1e-4, 2e-5)
+    # the unfused path (SpMM + dense layer) on the same inputs, and the autograd path, agree with it
+    with torch.no_grad():
+        os.environ['MGNNS_GCN_FUSED'] = '0'
+        try:
+            y2 = gc(x.to(dev), csr, act, slope)
+        finally:
+            del os.environ['MGNNS_GCN_FUSED']
+    close(y2, ref, 1e-4, 2e-5)
+    prev = ops.set_precision('tf32')
+    try:
+        with torch.no_grad():
+            y3 = gc(x.to(dev), csr, act, slope)
+    finally:
+        ops.set_precision(prev)
+    close(y3, ref, 2e-2, 5e-3)                           # plain TF32 operands: looser, stated bound
+
+
+def test_cfg2_bench_shape_matches_oracle_float64(ops, dev):
+    """BASELINE.json configs[1] at the bench shape — N=10,000 word graph (nnz = 650,000), 300 -> 512, ReLU — on a
+    64-sample chunk of the batch: the fused kernel AND the two-kernel path (2-D SpMM grid with rows_per_cta > 1,
+    79 x 2 tensor-core tiles per sample) against oracle.graph_convolution in float64 on four samples."""
+    from mgnns_b200.api.graph_util import CSRAdjacency
+    from mgnns_b200.api.multi_gcn import GraphConvolution
+    N, Fin, Fout, B = 10000, 300, 512, 64
+    rowptr, cols, val = synth.cfg2_word_graph(N, seed=0)
+    assert cols.shape[0] == 650000
+    csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, N, dev)
+    torch.manual_seed(0)
+    gc = GraphConvolution(Fin, Fout).to(dev)
+    x = torch.randn(B, N, Fin, generator=torch.Generator().manual_seed(5))
+    xd = x.to(dev)
+    A = torch.zeros(N, N, dtype=torch.float64)
+    A[torch.from_numpy(np.repeat(np.arange(N), np.diff(rowptr))), torch.from_numpy(cols)] = torch.from_numpy(val).double()
+    w64 = gc.weight.detach().cpu().double()
+    picks = (0, 1, 37, B - 1)
+    refs = {b: torch.relu(O.graph_convolution(x[b].double(), A, w64)) for b in picks}
+    with torch.no_grad():
+        y_fused = gc(xd, csr, ops.ACT_RELU)
+        os.environ['MGNNS_GCN_FUSED'] = '0'
+        try:
+            y_two = gc(xd, csr, ops.ACT_RELU)
+        finally:
+            del os.environ['MGNNS_GCN_FUSED']
+    for b in picks:
+        close(y_fused[b], refs[b], 1e-4, 1e-5)
+        close(y_two[b], refs[b], 1e-4, 1e-5)
+    # every sample, not just the four: the two implementations agree with each other to fp32 rounding
+    assert (y_fused - y_two).abs().max().item() < 2e-5
 
 
 # ------------------------------------------------------------------------------------------- text GCN
@@ -652,10 +749,8 @@ def test_full_model_logits_and_grads_vs_reference_golden(dev, golden):
     cfg = H.MODEL_CFG
     model = build_model(dev, cfg, H.edge_map_from_golden(zp, cfg['V']), int(zp['count'])).eval()
     text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
-    # eval-mode gradients: cuDNN's RNN backward refuses eval mode, so the (out-of-scope) LSTM runs on
-    # torch's native kernels for this check
-    with torch.backends.cudnn.flags(enabled=False):
-        logits = model(text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    # eval-mode forward + gradients (the bi-LSTM is the hand-written recurrence kernel, so no cuDNN eval-mode caveat)
+    logits = model(text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
     close(model.text_features(text.to(dev)), z['text_feature'], 1e-4, 1e-5)
     # north-star tolerance, fp32 mode
     close(logits, z['logits'], 1e-3, 1e-4)
