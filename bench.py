@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """MGNNS hot-path benchmark (contract: see the task statement / DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg5]
 
 A "step" is one training step of the MGNNS head (SURVEY §8d cfg 4): forward + CrossEntropy +
 backward + (gradient all-reduce when N>1) + clip_grad_norm_(10) + Adam, on a synthetic TumEmo-shaped
@@ -28,9 +28,17 @@ UNIT = "samples/s"
 VOCAB = 20154
 CFG = dict(ngram=4, n_head=4, d_kv=128, stack_num=2, hidden_size=150, num_layers=2, object_t=0.4, place_t=0.3,
            num_labels=7, L=100)
-WORKLOAD = ("cfg4 MGNNS head training step: TumEmo-shaped synthetic batch, %d samples/GPU, feature maps "
-            "[B,2048,14,14] x2 + text [B,100], V=20154, 7 labels; fwd+CE+bwd+clip_grad_norm+Adam; "
-            "ResNet trunks excluded (inputs are trunk outputs)")
+# BASELINE.json configs[3] (the headline: cfg 4) and configs[4] (stress: cfg 5)
+WORKLOADS = {
+    'cfg4': dict(V=VOCAB, n_obj=80, n_plc=365, n_head=4, docs=20000, object_t=0.4, place_t=0.3,
+                 name="cfg4 MGNNS head training step: TumEmo-shaped synthetic batch, %d samples/GPU, feature maps "
+                      "[B,2048,14,14] x2 + text [B,100], V=20154, 7 labels; fwd+CE+bwd+clip_grad_norm+Adam; "
+                      "ResNet trunks excluded (inputs are trunk outputs)"),
+    'cfg5': dict(V=50000, n_obj=4096, n_plc=4096, n_head=16, docs=200000, object_t=0.04, place_t=0.04,
+                 name="cfg5 stress training step: %d samples/GPU, V=50000 word graph (PMI counted on the GPU), 4096 object "
+                      "+ 4096 scene label nodes (A_hat 0.4% full), 16 attention heads; fwd+CE+bwd+clip+Adam; trunks excluded"),
+}
+WORKLOAD = WORKLOADS['cfg4']['name']
 
 
 def parse():
@@ -39,7 +47,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=512, help='samples per GPU')
+    ap.add_argument('--no-extras', action='store_true', help='skip the cfg-2 / cfg-3 / PMI / full-model legs of the N=1 line')
     ap.add_argument('--cpu-batch', type=int, default=32, help='samples per CPU-baseline step (cfg 1)')
     ap.add_argument('--no-cfg2', action='store_true', help='skip the cfg-2 GraphConvolution microbench')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -49,7 +59,13 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(steps, warmup, batch, seed=0):
+def label_adj(kind, n):
+    from mgnns_b200 import synth
+    default = 80 if kind == 'object' else 365
+    return synth.adj_dict(kind) if n == default else synth.synthetic_label_graph(n, seed=default)
+
+
+def cpu_reference_run(steps, warmup, batch, seed=0, workload='cfg4'):
     """The reference's algorithm for the same step on the host cores: the oracle port (oracle/), all
     threads.  The reference itself is pure Python/torch and cannot travel to the GPU box, and it has
     no compilable sources, so oracle/_ref does not exist for this repo."""
@@ -59,8 +75,11 @@ def cpu_reference_run(steps, warmup, batch, seed=0):
     from oracle import mgnns_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = dict(CFG, V=VOCAB, B=batch, seed=seed)
-    emap, count = synth.synthetic_edge_map(VOCAB, seed=0, docs=20000)
+    wl = WORKLOADS[workload]
+    V = wl['V']
+    cfg = dict(CFG, V=V, B=batch, seed=seed, n_head=wl['n_head'], n_obj=wl['n_obj'], n_plc=wl['n_plc'],
+               object_t=wl['object_t'], place_t=wl['place_t'])
+    emap, count = synth.synthetic_edge_map(V, seed=0, docs=20000)
     P = H.oracle_params(cfg, count)
     stepped = ('text_features.', 'gc1.', 'gc2.', 'object_attention.', 'place_attention.', 'lstm.',
                'img_object_text_multi_head_att.', 'img_place_text_multi_head_att.',
@@ -74,9 +93,9 @@ def cpu_reference_run(steps, warmup, batch, seed=0):
     edge_id = lambda u, v: emap[u, v]   # noqa: E731
     times = []
     for it in range(warmup + steps):
-        text, lens, mask = synth.make_texts(batch, VOCAB, CFG['L'], seed=seed + it)
+        text, lens, mask = synth.make_texts(batch, V, CFG['L'], seed=seed + it)
         fo, fp = synth.make_fmaps(batch, seed=2 * it), synth.make_fmaps(batch, seed=2 * it + 1)
-        oinp, pinp = synth.label_inputs(1)
+        oinp, pinp = synth.label_inputs(1, wl['n_obj'], wl['n_plc'])
         labels = synth.make_labels(batch, 7, seed=it)
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
@@ -90,8 +109,10 @@ def cpu_reference_run(steps, warmup, batch, seed=0):
             times.append(dt)
     sec = sum(times) / len(times)
     return dict(value=batch / sec, unit=UNIT, cores=cores, kind="port",
-                sample="%d steps of %d samples (cfg 1 batch) of the same head training step, fp32, "
-                       "torch CPU with %d threads; text channel via the oracle's per-document loop" % (steps, batch, cores),
+                sample="%d steps x %d samples (cfg 1 batch) of the same %s head step, fp32 torch CPU, %d threads"
+                       % (steps, batch, workload, cores),
+                note="oracle port, not the reference's modules: closed-form label attention (the reference's O(B^2) cat loop "
+                     "would be slower), per-document Python loop for the text channel kept",
                 ms_per_step=sec * 1e3)
 
 
@@ -101,12 +122,13 @@ def reference_arm(args):
         return
     steps = max(1, min(args.steps, 10))
     warm = max(1, min(args.warmup, 2))
-    r = cpu_reference_run(steps, warm, args.cpu_batch)
+    r = cpu_reference_run(steps, warm, args.cpu_batch, workload=args.workload)
     line = {"impl": "reference", "metric": METRIC, "value": r['value'], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": r['ms_per_step'], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % args.batch, "cpu_step_batch": args.cpu_batch},
-            "cpu_baseline": {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            "config": {"workload": WORKLOADS[args.workload]['name'] % args.batch, "cpu_step_batch": args.cpu_batch,
+                       "note": "one CPU process on the host cores whatever --gpus says (N>1: rank 0 only)"},
+            "cpu_baseline": {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'note')},
             "e2e": {"value": r['value'], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print_json(line)
@@ -155,38 +177,77 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_model(dev, emap, count):
+def make_edge_map(wl, dev=None):
+    """PMI edge-id map of the workload's vocabulary.  cfg 4: the same synthetic-corpus map the CPU arm builds
+    (host numpy, setup only).  cfg 5: V=50k — counted by the product path (mgnns_b200.api.pmi, table-free GPU count)."""
+    from mgnns_b200 import synth
+    if wl['V'] == VOCAB or dev is None:
+        return synth.synthetic_edge_map(wl['V'], seed=0, docs=20000)
+    from mgnns_b200.api import pmi
+    ids, _, _ = synth.make_texts(wl['docs'], wl['V'], CFG['L'], seed=101)
+    _, emap, count = pmi.cal_PMI_from_ids(ids.to('cuda').to(__import__('torch').int32), 0, wl['V'], 6, 2, device=dev)
+    return emap, count
+
+
+def build_model(dev, emap, count, wl=None, num_labels=7, trunks=None):
     import torch
     from mgnns_b200 import synth
     from mgnns_b200.api.multi_gcn import IdentityTrunk, Multi_GCN_Multihead_Att
     from mgnns_b200.api.text_gcn import Model as TextModel
-    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, VOCAB)]
-    tm = TextModel(7, 300, vocab, CFG['ngram'], 0.5, count, emap, pmi=torch.zeros(count, 1))
+    wl = wl or WORKLOADS['cfg4']
+    V = wl['V']
+    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, V)]
+    tm = TextModel(num_labels, 300, vocab, CFG['ngram'], 0.5, count, emap, pmi=torch.zeros(count, 1))
     opt = dict(emb_path='', bidirectional=True, hidden_size=150, emb_size=300, num_layers=2, dropout=0.5,
-               emb_type='random', vocab_size=VOCAB, stack_num=2, n_head=4, d_kv=128, is_regu=False)
-    model = Multi_GCN_Multihead_Att(opt, 7, tm, IdentityTrunk(), IdentityTrunk(), 80, 365, object_t=0.4,
-                                    place_t=0.3, in_channel=300, object_adj_file=synth.adj_dict('object'),
-                                    place_adj_file=synth.adj_dict('place'))
-    synth.fill_parameters(model, seed=0)
+               emb_type='random', vocab_size=V, stack_num=2, n_head=wl['n_head'], d_kv=128, is_regu=False)
+    obj_t, plc_t = trunks if trunks is not None else (IdentityTrunk(), IdentityTrunk())
+    model = Multi_GCN_Multihead_Att(opt, num_labels, tm, obj_t, plc_t, wl['n_obj'], wl['n_plc'], object_t=wl['object_t'],
+                                    place_t=wl['place_t'], in_channel=300, object_adj_file=label_adj('object', wl['n_obj']),
+                                    place_adj_file=label_adj('place', wl['n_plc']))
+    if trunks is None:
+        synth.fill_parameters(model, seed=0)
+    else:       # keep torchvision's own initialisation for the trunks
+        head = {k: v for k, v in model.state_dict().items() if not k.startswith(('object_features.', 'place_features.'))}
+        synth.fill_parameters(head, seed=0)
+        with torch.no_grad():
+            model.embedding.weight[0].zero_()
     return model.to(dev)
 
 
-def host_batch(B, seed):
+def host_batch(B, seed, wl=None, num_labels=7, images=False):
     """One step's inputs in pinned host memory, as the reference's DataLoader would hand them over
     (label-node matrices once, not replicated B times)."""
+    import torch
     from mgnns_b200 import synth
-    text, lens, mask = synth.make_texts(B, VOCAB, CFG['L'], seed=seed)
-    fo, fp = synth.make_fmaps(B, seed=2 * seed), synth.make_fmaps(B, seed=2 * seed + 1)
-    oinp, pinp = synth.label_inputs(1)
-    labels = synth.make_labels(B, 7, seed=seed)
-    d = dict(text=text, mask=mask, fo=fo, fp=fp, oinp=oinp.contiguous(), pinp=pinp.contiguous(), labels=labels)
+    wl = wl or WORKLOADS['cfg4']
+    text, lens, mask = synth.make_texts(B, wl['V'], CFG['L'], seed=seed)
+    if images:
+        g = torch.Generator().manual_seed(31 + seed)
+        fo = torch.randn(B, 3, 448, 448, generator=g)
+        fp = fo
+    else:
+        fo, fp = synth.make_fmaps(B, seed=2 * seed), synth.make_fmaps(B, seed=2 * seed + 1)
+    oinp, pinp = synth.label_inputs(1, wl['n_obj'], wl['n_plc'])
+    labels = synth.make_labels(B, num_labels, seed=seed)
+    d = dict(text=text, mask=mask, fo=fo, oinp=oinp.contiguous(), pinp=pinp.contiguous(), labels=labels)
+    if not images:
+        d['fp'] = fp
     d = {k: v.pin_memory() for k, v in d.items()}
+    if images:
+        d['fp'] = d['fo']                       # the same image feeds both trunks (engine:861-862): one H2D copy
     d['lens'] = lens
     return d
 
 
 def to_device(hb, dev, B):
-    d = {k: (v.to(dev, non_blocking=True) if k != 'lens' else v) for k, v in hb.items()}
+    d = {}
+    for k, v in hb.items():
+        if k == 'lens':
+            d[k] = v
+        elif k == 'fp' and hb['fp'] is hb['fo']:
+            d[k] = d['fo']
+        else:
+            d[k] = v.to(dev, non_blocking=True)
     d['oinp_base'], d['pinp_base'] = d['oinp'], d['pinp']
     d['oinp'] = d['oinp_base'].expand(B, -1, -1)
     d['pinp'] = d['pinp_base'].expand(B, -1, -1)
@@ -194,12 +255,51 @@ def to_device(hb, dev, B):
 
 
 def h2d_bytes(hb):
-    return int(sum(v.numel() * v.element_size() for k, v in hb.items() if k != 'lens'))
+    seen, total = set(), 0
+    for k, v in hb.items():
+        if k != 'lens' and v.data_ptr() not in seen:
+            seen.add(v.data_ptr())
+            total += v.numel() * v.element_size()
+    return int(total)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first touch) to the CPUs NVML
+    reports as local to GPU `index`, so the H2D copies of different ranks do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d" % (len(cpus), index)
+        return "no local cpus reported"
+    except Exception as exc:                 # topology information is best effort
+        return "unavailable: %s" % str(exc)[:80]
+
+
+def _time_ms(fn, iters, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def gcn_cfg2_microbench(dev, peaks):
-    """SURVEY §8d cfg 2: one GraphConvolution(300,512)+ReLU, N=10,000 PMI-like word graph (power-law
-    degrees, mean 64 + self loop), X f32[256,10000,300] -> f32[256,10000,512]."""
+    """SURVEY §8d cfg 2: one GraphConvolution(300,512)+ReLU, N=10,000 PMI-like word graph (power-law degrees, mean 64 +
+    self loop: nnz = 650,000), X f32[256,10000,300] -> f32[256,10000,512].  Returns roofline objects for the layer and
+    for the SpMM kernel, and the fused single-kernel variant beside them."""
     import torch
     from mgnns_b200 import ops, synth
     from mgnns_b200.api.graph_util import CSRAdjacency
@@ -211,85 +311,175 @@ def gcn_cfg2_microbench(dev, peaks):
     x = torch.randn(B, N, Fin, device=dev)
     nnz = int(cols.shape[0])
     alg_bytes = 4 * (B * N * Fin + B * N * Fout + Fin * Fout) + 8 * nnz + 4 * (N + 1)
-    with torch.no_grad():
-        for _ in range(2):
-            y = gc(x, csr, ops.ACT_RELU)
-        ops.KernelTimers.reset(['spmm_csr', 'linear_tc'])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 5
-        e0.record()
-        for _ in range(iters):
-            y = gc(x, csr, ops.ACT_RELU)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    spmm_ms, _ = ops.KernelTimers.mean_ms('spmm_csr')
-    lin_ms, _ = ops.KernelTimers.mean_ms('linear_tc')
-    ops.KernelTimers.reset([])
     spmm_bytes = 4 * (2 * B * N * Fin) + 8 * nnz
     dense_flop = 2.0 * B * N * Fin * Fout
-    del x, y
+    out = {}
+    with torch.no_grad():
+        os.environ['MGNNS_GCN_FUSED'] = '0'
+        ops.KernelTimers.reset(['spmm_csr', 'spmm_hub', 'linear_tc'])
+        ms = _time_ms(lambda: gc(x, csr, ops.ACT_RELU), 5)
+        spmm_ms = ops.KernelTimers.mean_ms('spmm_hub')[0] or ops.KernelTimers.mean_ms('spmm_csr')[0]
+        lin_ms, _ = ops.KernelTimers.mean_ms('linear_tc')
+        ops.KernelTimers.reset([])
+        os.environ['MGNNS_GCN_FUSED'] = '1'
+        try:
+            fused_ms = _time_ms(lambda: gc(x, csr, ops.ACT_RELU), 3)
+        except Exception as exc:
+            fused_ms = None
+            out['fused_error'] = str(exc)[:100]
+        os.environ['MGNNS_GCN_FUSED'] = '0'
+    del x
     torch.cuda.empty_cache()
     tf32_peak = peaks['bf16_tflops_sustained'] / 2.0
-    return {"workload": "cfg2 GraphConvolution(300->512)+ReLU, N=10000, nnz=%d, batch 256, fp32 in/out" % nnz,
-            "precision_mode": ops.get_precision(),
-            "ms_per_call": ms, "algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / ms / 1e6,
-            "frac_of_measured_hbm": alg_bytes / ms / 1e6 / peaks['hbm_gbs'],
-            "frac_of_8TBs": alg_bytes / ms / 1e6 / 8000.0,
-            "spmm_kernel_ms": spmm_ms, "spmm_kernel_gbs": (spmm_bytes / spmm_ms / 1e6) if spmm_ms else None,
-            "spmm_gather_tbs": (4.0 * nnz * B * Fin / spmm_ms / 1e9) if spmm_ms else None,
-            "spmm_bound": "L2->SM gather bandwidth (nnz x batch x 1200 B per call; X_b is L2-resident), not HBM",
-            "dense_kernel": "tc_linear_kernel (tcgen05, TMA, TMEM)", "dense_kernel_ms": lin_ms,
-            "dense_tflops": (dense_flop / lin_ms / 1e9) if lin_ms else None,
-            "dense_frac_of_tf32_peak": (dense_flop / lin_ms / 1e9 / tf32_peak) if lin_ms else None,
-            "dense_gflop": dense_flop / 1e9, "sparse_gflop": 2.0 * B * nnz * Fin / 1e9}
+    hbm = peaks['hbm_gbs']
+    out.update({
+        "gcn_layer_cfg2": {"kernel": "spmm + tc_linear (GraphConvolution 300->512 + ReLU, N=10000, nnz=%d, batch 256)" % nnz,
+                           "bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                           "frac": alg_bytes / ms / 1e6 / hbm, "frac_of_8TBs": alg_bytes / ms / 1e6 / 8000.0,
+                           "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg_bytes, "precision_mode": ops.get_precision(),
+                           "traffic": None,
+                           "note": "not HBM-bound: nnz x batch x 1200 B = %.0f GB of neighbour rows cross L2->SM per call" % (4.0 * nnz * B * Fin / 1e9)},
+        "spmm_cfg2": {"kernel": "spmm (A_hat.X, 300 wide)", "bound": "hbm", "achieved": spmm_bytes / spmm_ms / 1e6 if spmm_ms else None,
+                      "peak": hbm, "unit": "GB/s", "frac": (spmm_bytes / spmm_ms / 1e6 / hbm) if spmm_ms else None,
+                      "ms_per_launch": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes,
+                      "gather_tbs": (4.0 * nnz * B * Fin / spmm_ms / 1e9) if spmm_ms else None,
+                      "note": "bound by L2->SM gather bandwidth (measured fabric limit ~16-18 TB/s), X_b is L2-resident"},
+        "dense_cfg2": {"kernel": "tc_linear_kernel (tcgen05, TMA, TMEM; 3xTF32)", "bound": "tensor",
+                       "achieved": (dense_flop / lin_ms / 1e9) if lin_ms else None, "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": (dense_flop / lin_ms / 1e9 / tf32_peak) if lin_ms else None, "ms_per_launch": lin_ms,
+                       "mma_work_factor": 3.0 if ops.get_precision() == 'tf32x3' else 1.0},
+        "gcn_fused_cfg2": {"kernel": "gcn_fused_kernel (gather -> smem operand -> tcgen05, Z never in HBM; opt-in)",
+                           "bound": "hbm", "achieved": (alg_bytes / fused_ms / 1e6) if fused_ms else None, "peak": hbm,
+                           "unit": "GB/s", "frac": (alg_bytes / fused_ms / 1e6 / hbm) if fused_ms else None,
+                           "ms_per_launch": fused_ms},
+    })
+    return out
 
 
-def pmi_microbench(dev, peaks, docs=200000, cpu_docs=4000):
-    """§8 row a1 (ref: utils/pmi.py:40-58): windowed co-occurrence counts of a synthetic TumEmo-shaped corpus
-    (200k docs x 100 padded tokens, V=20,154, window 6, min co-occurrence 2) on the GPU — dense int32 count table
-    + ordered CSR compaction — beside the oracle's vectorised numpy port on a bounded sample."""
+def pmi_microbench(dev, peaks, V=VOCAB, docs=200000, cpu_docs=4000):
+    """§8 row a1 (ref: utils/pmi.py:37-66): windowed co-occurrence counts of a synthetic TumEmo-shaped corpus (200k docs
+    x 100 padded tokens, window 6, min co-occurrence 2) on the GPU, table-free, beside the oracle's numpy port on a
+    bounded sample (which is also checked bit-exact against the GPU counts of the same documents)."""
     import numpy as np
     import torch
     from mgnns_b200 import ops, synth
     from oracle import pmi_oracle as PO
-    text, lens, _ = synth.make_texts(docs, VOCAB, CFG['L'], seed=7)
+    text, lens, _ = synth.make_texts(docs, V, CFG['L'], seed=7)
     tok = text.to(torch.int32).to(dev)
-    for _ in range(2):
-        out = ops.pmi_count(tok, VOCAB, 6, 0, 2)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    iters = 3
-    for _ in range(iters):
-        rowptr, col, cnt, wc = ops.pmi_count(tok, VOCAB, 6, 0, 2)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    ms = _time_ms(lambda: ops.pmi_count(tok, V, 6, 0, 2), 3)
+    rowptr, col, cnt, wc = ops.pmi_count(tok, V, 6, 0, 2)
+    pairs = int(ops.pmi_count.last_pairs)
     live = int(lens.clamp(max=CFG['L']).sum())
-    ids = text[:cpu_docs].numpy()
-    t0 = time.perf_counter()
-    pair, wc_cpu = PO.counts_numpy(ids, 0, VOCAB, 6)
-    cpu_s = time.perf_counter() - t0
-    # bit-exactness of the sample (checker only): GPU counts of the same documents
-    r2, c2, n2, w2 = ops.pmi_count(tok[:cpu_docs].contiguous(), VOCAB, 6, 0, 1)
-    rows = np.repeat(np.arange(VOCAB), np.diff(r2.cpu().numpy().astype(np.int64)))
-    dense = np.zeros_like(pair)
-    dense[rows, c2.cpu().numpy().astype(np.int64)] = n2.cpu().numpy()
-    exact = bool(np.array_equal(dense, pair) and np.array_equal(w2.cpu().numpy(), wc_cpu))
-    del pair, dense
-    table_bytes = 4.0 * VOCAB * VOCAB
-    return {"workload": "PMI co-occurrence counts: %d docs x 100 tokens (%d non-pad), V=%d, window 6, min_cooccurence 2"
-                        % (docs, live, VOCAB),
-            "gpu_ms": ms, "docs_per_s": docs / ms * 1e3, "kept_cells": int(col.numel()),
-            "hbm_bytes": 3 * table_bytes + 4.0 * docs * CFG['L'],
-            "hbm_gbs": (3 * table_bytes + 4.0 * docs * CFG['L']) / ms / 1e6,
-            "frac_of_measured_hbm": (3 * table_bytes + 4.0 * docs * CFG['L']) / ms / 1e6 / peaks['hbm_gbs'],
-            "bytes_note": "dense int32 [V,V] table zeroed, scanned for row counts and scanned again for the ordered CSR fill",
-            "cpu_port": {"docs": cpu_docs, "seconds": cpu_s, "docs_per_s": cpu_docs / cpu_s, "cores": 1,
-                         "kind": "port (oracle/pmi_oracle.counts_numpy)"},
-            "sample_bit_exact": exact}
+    exact = None
+    cpu = None
+    if V <= 25000:
+        ids = text[:cpu_docs].numpy()
+        t0 = time.perf_counter()
+        pair, wc_cpu = PO.counts_numpy(ids, 0, V, 6)
+        cpu_s = time.perf_counter() - t0
+        r2, c2, n2, w2 = ops.pmi_count(tok[:cpu_docs].contiguous(), V, 6, 0, 1)
+        rows = np.repeat(np.arange(V), np.diff(r2.cpu().numpy().astype(np.int64)))
+        dense = np.zeros_like(pair)
+        dense[rows, c2.cpu().numpy().astype(np.int64)] = n2.cpu().numpy()
+        exact = bool(np.array_equal(dense, pair) and np.array_equal(w2.cpu().numpy(), wc_cpu))
+        cpu = {"docs": cpu_docs, "seconds": cpu_s, "docs_per_s": cpu_docs / cpu_s, "cores": 1,
+               "kind": "port (oracle/pmi_oracle.counts_numpy)"}
+        del pair, dense
+    # algorithmic bytes: tokens read twice (count, scatter), every emitted pair written once and read once (4 B),
+    # kept cells written once (8 B) and copied once into the final CSR (8 B read + 8 B written)
+    alg = 2 * 4.0 * docs * CFG['L'] + 8.0 * pairs + 24.0 * int(col.numel())
+    return {"kernel": "pmi_count (row emissions, scatter, per-row smem counters, compaction), V=%d, %d docs, %d pairs" % (V, docs, pairs),
+            "bound": "hbm", "achieved": alg / ms / 1e6, "peak": peaks['hbm_gbs'], "unit": "GB/s",
+            "frac": alg / ms / 1e6 / peaks['hbm_gbs'], "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg,
+            "docs_per_s": docs / ms * 1e3, "live_tokens": live, "kept_cells": int(col.numel()), "cpu_port": cpu,
+            "sample_bit_exact": exact, "traffic": None,
+            "note": "integer atomics + shared-memory counters; latency/atomic bound, not HBM bound"}
+
+
+def cfg3_inference_leg(dev, emap, count, peaks, B=1024):
+    """BASELINE.json configs[2]: full-head inference, batch 1024, MVSA-Single-shaped (3 classes) and TumEmo-shaped
+    (7 classes), eval mode, no grad; device-resident samples/s and end to end from pinned host buffers."""
+    import torch
+    res = {}
+    for C in (7, 3):
+        model = build_model(dev, emap, count, WORKLOADS['cfg4'], num_labels=C).eval()
+        model.branch_streams = True
+        hbs = [host_batch(B, seed=700 + i, num_labels=C) for i in range(2)]
+        dbs = [to_device(hb, dev, B) for hb in hbs]
+        torch.cuda.synchronize()
+        state = {'i': 0}
+
+        def step():
+            d = dbs[state['i'] % 2]
+            state['i'] += 1
+            with torch.no_grad():
+                return model(d['text'], d['lens'], d['mask'], d['fo'], d['fp'], d['oinp'], d['pinp'])
+        ms = _time_ms(step, 10, warm=3)
+        # end to end: H2D of each batch (copy stream, prefetch depth 1) + argmax read back
+        copy = torch.cuda.Stream(device=dev)
+
+        def prefetch(i):
+            hb, d = hbs[i % 2], dbs[i % 2]
+            with torch.cuda.stream(copy):
+                for k in ('text', 'mask', 'fo', 'fp', 'labels'):
+                    d[k].copy_(hb[k], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return ev
+        E = 6
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev = prefetch(0)
+        for i in range(E):
+            torch.cuda.current_stream().wait_event(ev)
+            state['i'] = i
+            logits = step()
+            if i + 1 < E:
+                ev = prefetch(i + 1)
+            pred = logits.argmax(1).cpu()
+        e2e_s = time.perf_counter() - t0
+        alg = B * (2 * 2048 * 196 * 4 + 100 * 300 * 4 + 100 * 12)            # SURVEY §8d: 3.33 MB/sample
+        res["C%d" % C] = {"samples_per_s": B / ms * 1e3, "ms_per_batch": ms, "e2e_samples_per_s": B * E / e2e_s,
+                          "hbm_gbs": alg / ms / 1e6, "frac_of_measured_hbm": alg / ms / 1e6 / peaks['hbm_gbs'],
+                          "h2d_bytes_per_batch": h2d_bytes(hbs[0]), "pred_hist": torch.bincount(pred, minlength=C).tolist()}
+        del model, dbs, hbs
+        torch.cuda.empty_cache()
+    res["workload"] = "cfg3 full-head inference, batch %d, eval/no-grad, feature maps in (trunks excluded)" % B
+    return res
+
+
+def full_model_leg(dev, emap, count, B=32, steps=4):
+    """the FULL model — images [B,3,448,448] -> ResNet-101 + ResNet-50/365 trunks (torchvision/cuDNN, random
+    init) -> the hand-written head — as a training step, reported separately from the head-only headline."""
+    import torch
+    import torchvision.models as models
+    model = build_model(dev, emap, count, WORKLOADS['cfg4'],
+                        trunks=(models.resnet101(weights=None), models.resnet50(weights=None, num_classes=365))).train()
+    opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5, fused=True)
+    crit = torch.nn.CrossEntropyLoss()
+    hb = host_batch(B, seed=900, images=True)
+    d = to_device(hb, dev, B)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(d['text'], d['lens'], d['mask'], d['fo'], d['fp'], d['oinp'], d['pinp']), d['labels'])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
+        opt.step()
+        return loss
+    ms = _time_ms(step, steps, warm=2)
+    model.eval()
+
+    def infer():
+        with torch.no_grad():
+            return model(d['text'], d['lens'], d['mask'], d['fo'], d['fp'], d['oinp'], d['pinp'])
+    ms_inf = _time_ms(infer, steps, warm=1)
+    del model, opt, d
+    torch.cuda.empty_cache()
+    return {"workload": "full model training step, batch %d: images [B,3,448,448] -> ResNet-101 + ResNet-50 (cuDNN, TF32 convs "
+                        "= torch default) -> head kernels; ~95 GFLOP/sample forward in the trunks" % B,
+            "train_samples_per_s": B / ms * 1e3, "train_ms_per_step": ms, "inference_samples_per_s": B / ms_inf * 1e3,
+            "trunks": "torchvision resnet101 + resnet50(365), random init"}
 
 
 def load_peaks():
@@ -306,14 +496,14 @@ def load_peaks():
 def ours(args):
     import torch
     import torch.distributed as dist
-    from mgnns_b200 import _abi, ops, synth
-    from mgnns_b200.ddp import GradientAllReducer
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    numa = bind_to_gpu_numa_node(local)         # before any pinned allocation
+    from mgnns_b200 import _abi, ops, synth
+    from mgnns_b200.ddp import GradientAllReducer
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -321,9 +511,11 @@ def ours(args):
         dist.init_process_group('nccl', device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     peaks = load_peaks()
+    wl = WORKLOADS[args.workload]
+    H_ = wl['n_head']
 
-    emap, count = synth.synthetic_edge_map(VOCAB, seed=0, docs=20000)
-    model = build_model(dev, emap, count).train()
+    emap, count = make_edge_map(wl, dev)
+    model = build_model(dev, emap, count, wl).train()
     model.branch_streams = not args.no_branch_streams
     use_graph = not args.eager
     # same optimiser and hyper-parameters as the reference entry script (entry:164); fused=True only selects torch's
@@ -332,8 +524,10 @@ def ours(args):
     reducer = GradientAllReducer(model) if (world > 1 and not use_graph) else None
     crit = torch.nn.CrossEntropyLoss()
 
-    # two distinct batches per rank (3.3 GB of inputs per pair >> 126 MB L2), alternating
-    hbs = [host_batch(B, seed=rank * 100 + i) for i in range(2)]
+    # three distinct batches per rank (1.65 GB of inputs each >> 126 MB L2), rotating; three so that the end-to-end loop can
+    # keep two host->device copies in flight (prefetch depth 2) while the third buffer is being read
+    NB = 3
+    hbs = [host_batch(B, seed=rank * 100 + i, wl=wl) for i in range(NB)]
     dbs = [to_device(hb, dev, B) for hb in hbs]
     torch.cuda.synchronize()
 
@@ -374,8 +568,8 @@ def ours(args):
 
     def run_step(i):
         if gsteps is not None:
-            return gsteps[i % 2].replay()
-        return step(dbs[i % 2])
+            return gsteps[i % NB].replay()
+        return step(dbs[i % NB])
 
     for i in range(W):
         run_step(i)
@@ -401,15 +595,30 @@ def ours(args):
     ms_step = t.item() / K
     value = world * B / (ms_step / 1e3)
 
-    # ---- end-to-end: pinned host inputs -> H2D (prefetched on a copy stream) -> step -> loss.item() -----
+    # exposed all-reduce: CUDA events around the eager NCCL call between the two captured halves (a few extra steps)
+    allreduce_ms = None
+    if world > 1 and gsteps is not None:
+        for g in gsteps:
+            g.time_allreduce, g.allreduce_events = True, []
+        for i in range(6):
+            run_step(i)
+        barrier()
+        ev = [a.elapsed_time(b) for g in gsteps for a, b in g.allreduce_events]
+        for g in gsteps:
+            g.time_allreduce, g.allreduce_events = False, []
+        t = torch.tensor([sum(ev) / max(len(ev), 1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_ms = t.item()
+
+    # ---- end-to-end: pinned host inputs -> H2D (prefetched on a copy stream, depth 2) -> step -> loss.item() -----
     copy_stream = torch.cuda.Stream(device=dev)
 
     def prefetch(i):
         """H2D of batch i into its static device buffers (+ its LSTM schedule), on the copy stream."""
-        hb, d = hbs[i % 2], dbs[i % 2]
+        hb, d = hbs[i % NB], dbs[i % NB]
         with torch.cuda.stream(copy_stream):
             if gsteps is not None:
-                gsteps[i % 2].update_lengths(hb['lens'])
+                gsteps[i % NB].update_lengths(hb['lens'])
             else:
                 model.make_text_plan(d['lens'], CFG['L'])
             for k, v in hb.items():
@@ -421,22 +630,37 @@ def ours(args):
             ev.record(copy_stream)
         return ev
 
+    # the H2D ceiling of this box for this rank's buffers, all ranks copying at once (what bounds e2e)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+        for i in range(4):
+            for k in ('fo', 'fp'):
+                dbs[i % NB][k].copy_(hbs[i % NB][k], non_blocking=True)
+        c1.record(copy_stream)
+    barrier()
+    h2d_ceiling = 4 * 2 * hbs[0]['fo'].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+
     for i in range(2):                      # warm the e2e path
         ev = prefetch(i)
         torch.cuda.current_stream().wait_event(ev)
         run_step(i).item()
     barrier()
-    E = max(4, K // 2)
+    E = max(6, K // 2)
     t0 = time.perf_counter()
-    ev = prefetch(0)
+    evs = {0: prefetch(0), 1: prefetch(1)}
+    done = {}
     for i in range(E):
-        torch.cuda.current_stream().wait_event(ev)
+        torch.cuda.current_stream().wait_event(evs.pop(i))
         loss = run_step(i)
-        done = torch.cuda.Event()
-        done.record()
-        if i + 1 < E:
-            # the other buffer was last read by step i-1, which has completed (loss.item() below syncs every step)
-            ev = prefetch(i + 1)
+        done[i] = torch.cuda.Event()
+        done[i].record()
+        if i + 2 < E:
+            # buffer (i+2) % 3 was last read by step i-1: the copy stream waits for that step, not the host
+            if i - 1 in done:
+                copy_stream.wait_event(done.pop(i - 1))
+            evs[i + 2] = prefetch(i + 2)
         loss_val = loss.item()              # device -> host read of the step's result
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -447,7 +671,8 @@ def ours(args):
     e2e_value = world * B * E / e2e_seconds
 
     # ---- per-kernel timing pass (eager, same inputs): CUDA events around the hand-written kernels -------
-    timer_names = ['imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd', 'lstm_rec_fwd', 'lstm_rec_bwd']
+    timer_names = ['imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd', 'lstm_rec_fwd', 'lstm_rec_bwd',
+                   'linear_tc', 'wgrad_tc', 'spmm_csr', 'text_maxagg_fwd', 'text_maxagg_bwd']
     opt_e = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5)
     red_e = GradientAllReducer(model) if world > 1 else None
     saved = (opt, reducer)
@@ -459,7 +684,7 @@ def ours(args):
     torch.cuda.synchronize()
     ops.KernelTimers.reset(timer_names)
     for i in range(KT):
-        step(dbs[i % 2])
+        step(dbs[i % NB])
     torch.cuda.synchronize()
     kt = {n: ops.KernelTimers.mean_ms(n) for n in timer_names}
     ops.KernelTimers.reset([])
@@ -472,82 +697,95 @@ def ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant hand-written kernel -------------------------------------------------
+    # ---- rooflines of the hand-written kernels (the dominant one is `roofline`, the others ride inside it) ---------------
     C, P_, O_ = 2048, 196, 300
-    cand = {n: (ms or 0.0) * cnt for n, (ms, cnt) in kt.items() if n in ('imgbank_fwd', 'imgbank_dw', 'rowmax', 'attn_q1_fwd', 'attn_q1_bwd')}
-    dom = max(cand, key=cand.get)
-    dom_ms, dom_cnt = kt[dom]
     flop = {'imgbank_fwd': 2.0 * B * P_ * C * O_, 'imgbank_dw': 2.0 * B * P_ * C * O_}
     byts = {'imgbank_fwd': 4.0 * (B * C * P_ + B * P_ * O_ + O_ * C), 'imgbank_dw': 4.0 * (B * C * P_ + B * P_ * O_ + O_ * C),
             'rowmax': 4.0 * (B * C * P_ + 2 * B * C),
+            # attention launches alternate between the image banks (L=196) and the text bank (L=100, masked: ~16 live rows)
             'attn_q1_fwd': 4.0 * B * (P_ + 100) / 2 * 300, 'attn_q1_bwd': 4.0 * B * (P_ + 100) * 300}
-    traffic = None
+    traffic_tbl = {}
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(dom, {}).get('dram_bytes_per_launch')
-    if dom in flop:
-        # fp32 CUDA-core GEMM today: the bound a tensor-core version will be held to is the TF32 pipe
-        # (half the measured dense bf16 rate)
-        peak = peaks['bf16_tflops_sustained'] / 2.0
-        ach = flop[dom] / (dom_ms * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": traffic, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
-                "share_of_step": dom_ms * dom_cnt / KT / ms_step,
-                "peak_source": peaks['source'] + "; TF32 = bf16_tflops_sustained/2",
-                "mma_work_factor": 3.0 * (224.0 / 196.0) * (304.0 / 300.0) if ops.get_precision() == 'tf32x3' else (224.0 / 196.0) * (304.0 / 300.0),
-                "mma_note": "3xTF32 issues 3 MMAs per algorithmic product, tiles pad 196->224 positions and 300->304 outputs: "
-                            "tensor-pipe utilisation = frac x mma_work_factor",
-                "algorithmic_flop_per_launch": flop[dom], "algorithmic_bytes_per_launch": byts[dom]}
-    else:
-        ach = byts[dom] / (dom_ms * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks['hbm_gbs'], "unit": "GB/s",
-                "frac": ach / peaks['hbm_gbs'], "traffic": traffic, "launches_timed": dom_cnt, "ms_per_launch": dom_ms,
-                "share_of_step": dom_ms * dom_cnt / KT / ms_step, "peak_source": peaks['source'],
-                "algorithmic_bytes_per_launch": byts[dom]}
-    kernels = {n: {"ms_per_launch": ms, "launches_per_step": cnt / KT,
-                   "gbs": (byts[n] / (ms * 1e-3) / 1e9) if (ms and n in byts) else None,
-                   "tflops": (flop[n] / (ms * 1e-3) / 1e12) if (ms and n in flop) else None}
-               for n, (ms, cnt) in kt.items()}
+            traffic_tbl = json.load(f)
+    tf32_peak = peaks['bf16_tflops_sustained'] / 2.0
+    mma_factor = (3.0 if ops.get_precision() == 'tf32x3' else 1.0) * (224.0 / 196.0) * (304.0 / 300.0)
+
+    def roof_of(n):
+        ms, cnt = kt[n]
+        if not ms:
+            return None
+        traffic = traffic_tbl.get(n, {}).get('dram_bytes_per_launch')
+        share = ms * cnt / KT / ms_step
+        if n in flop:
+            ach = flop[n] / (ms * 1e-3) / 1e12
+            return {"kernel": n, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                    "traffic": traffic, "launches_timed": cnt, "ms_per_launch": ms, "share_of_step": share,
+                    "peak_source": peaks['source'] + "; TF32 = bf16_tflops_sustained/2", "mma_work_factor": mma_factor,
+                    "algorithmic_flop_per_launch": flop[n], "algorithmic_bytes_per_launch": byts[n]}
+        if n in byts:
+            ach = byts[n] / (ms * 1e-3) / 1e9
+            return {"kernel": n, "bound": "hbm", "achieved": ach, "peak": peaks['hbm_gbs'], "unit": "GB/s",
+                    "frac": ach / peaks['hbm_gbs'], "traffic": traffic, "launches_timed": cnt, "ms_per_launch": ms,
+                    "share_of_step": share, "peak_source": peaks['source'], "algorithmic_bytes_per_launch": byts[n]}
+        return {"kernel": n, "ms_per_launch": ms, "launches_timed": cnt, "share_of_step": share}
+
+    roofs = {n: roof_of(n) for n in timer_names}
+    roofs = {n: r for n, r in roofs.items() if r}
+    cand = {n: r['share_of_step'] for n, r in roofs.items() if 'frac' in r}
+    dom = max(cand, key=cand.get)
+    roof = dict(roofs[dom])
+    roof["mma_note"] = "3xTF32 = 3 MMAs per product, tiles pad 196->224 and 300->304: tensor-pipe use = frac x mma_work_factor"
+    roof["others"] = {n: r for n, r in roofs.items() if n != dom}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % B, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": "dp%d" % world,
-                       "l2": "inputs larger than L2 (1.65 GB of feature maps per step; two alternating batches)",
-                       "precision_mode": "%s for the image-bank contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
+            "config": {"workload": wl['name'] % B, "workload_id": args.workload, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": "dp%d" % world, "n_head": H_, "vocab": wl['V'], "label_nodes": [wl['n_obj'], wl['n_plc']],
+                       "l2": "inputs larger than L2 (1.65 GB of feature maps per step; three rotating batches)",
+                       "precision_mode": "%s tensor-core contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
                        "launch": launch_mode, "launch_note": graph_note, "branch_streams": bool(model.branch_streams),
-                       "kernel_timing": "per-kernel numbers from a separate eager, single-stream pass of %d steps on the same inputs (CUDA events around each launch)" % KT},
+                       "numa": numa,
+                       "kernel_timing": "per-kernel: separate eager single-stream pass of %d steps, CUDA events per launch" % KT},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(hbs[0]),
                     "d2h_bytes_per_step": 4, "steps": E, "last_loss": loss_val,
-                    "how": "pinned host batch -> H2D on a copy stream (prefetch depth 1) -> model/backward/"
-                           "clip/Adam through the nn.Module API -> loss.item()",
+                    "how": "pinned host batch -> H2D on a copy stream (prefetch depth 2) -> nn.Module step -> loss.item()",
                     "h2d_gbs_per_gpu": h2d_bytes(hbs[0]) * E / e2e_seconds / 1e9,
-                    "bound": "host->device copy of the fp32 feature maps (1.6 GB per 512-sample step per GPU); "
-                             "the device-resident step is shorter than the copy"},
+                    "h2d_ceiling_gbs_per_gpu": h2d_ceiling,
+                    "bound": "host->device copy of the fp32 feature maps (1.6 GB per step per GPU): e2e/ceiling = %.2f"
+                             % (h2d_bytes(hbs[0]) * E / e2e_seconds / 1e9 / h2d_ceiling)},
             "gpu_launches": int(launches),
-            "roofline": roof, "kernels": kernels}
+            "roofline": roof}
     if world > 1:
         line["allreduce_payload_bytes"] = payload
+        line["e2e"]["allreduce_exposed_ms"] = allreduce_ms
+        line["config"]["allreduce_exposed_ms"] = allreduce_ms
         dist.destroy_process_group()
     if world == 1:
-        del dbs
+        del dbs, gsteps
         torch.cuda.empty_cache()
-        if not args.no_cfg2:
-            try:
-                line["gcn_layer_cfg2"] = gcn_cfg2_microbench(dev, peaks)
-            except Exception as exc:       # keep the headline line even if the microbench cannot allocate
-                line["gcn_layer_cfg2"] = {"error": str(exc)[:200]}
-        if not args.no_cfg2:
-            try:
-                line["pmi_count"] = pmi_microbench(dev, peaks)
-            except Exception as exc:
-                line["pmi_count"] = {"error": str(exc)[:200]}
+        extras = {}
+        if not (args.no_cfg2 or args.no_extras):
+            for name, fn in (("cfg2", lambda: gcn_cfg2_microbench(dev, peaks)), ("pmi_count", lambda: {"pmi_count": pmi_microbench(dev, peaks)}),
+                             ("pmi_count_v50k", lambda: {"pmi_count_v50k": pmi_microbench(dev, peaks, V=50000)})):
+                try:
+                    line["roofline"]["others"].update(fn())
+                except Exception as exc:       # keep the headline line even if a microbench cannot allocate
+                    line["roofline"]["others"][name] = {"error": str(exc)[:200]}
+        if not args.no_extras and args.workload == 'cfg4':
+            for name, fn in (("cfg3_inference", lambda: cfg3_inference_leg(dev, emap, count, peaks)),
+                             ("full_model", lambda: full_model_leg(dev, emap, count))):
+                try:
+                    extras[name] = fn()
+                except Exception as exc:
+                    extras[name] = {"error": str(exc)[:200]}
+            line["config"]["other_configs"] = extras
         if not args.no_cpu_baseline:
-            r = cpu_reference_run(3, 1, args.cpu_batch)
-            line["cpu_baseline"] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            r = cpu_reference_run(3, 1, args.cpu_batch, workload=args.workload)
+            line["cpu_baseline"] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'note')}
     print_json(line)
 
 

@@ -278,6 +278,44 @@ int mgnns_count_row_nnz_i32(const int32_t* M, int n_rows, int n_cols, int min_co
 int mgnns_count_fill_csr_i32(const int32_t* M, int n_rows, int n_cols, int min_count,
                              const int32_t* rowptr, int32_t* col, int32_t* cnt, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * PMI co-occurrence counts without the dense [V,V] table (the product path; the dense-table entry points above
+ * remain for small vocabularies and as a cross-check).  Steps, all on `stream`:
+ *   mgnns_pmi_row_emissions   row_emit[c] = number of (centre c -> target) pairs, word_count[c] (both zeroed here)
+ *   mgnns_exclusive_scan_i64  row_start[V+1]
+ *   mgnns_pmi_scatter_targets targets[row_start[c] ...] = the row's targets in arrival order (cursor zeroed here)
+ *   mgnns_pmi_row_reduce      per centre row: shared-memory column counters, cells >= min_count written in column
+ *                             order to tmp_col/tmp_cnt at row_start[c] (at most as many as emissions), row_nnz[c]
+ *   mgnns_pmi_compact         tmp -> CSR col/cnt at rowptr (int32 scan of row_nnz by mgnns_exclusive_scan_i32)
+ * Only centres in [row_lo,row_hi) are counted (row sharding across ranks: disjoint row ranges need no reduction).
+ * A cell's count is bounded by its row's emission count; callers check max(row_emit) < 2^31 (cells are int32).
+ * ref: utils/pmi.py:37-66 (pair_count / word_count loops and the min_cooccurence filter), :89-97 (row-major ids)
+ * ------------------------------------------------------------------------- */
+int mgnns_pmi_row_emissions(const int32_t* tokens, int64_t D, int L, int V, int window, int pad_id,
+                            int row_lo, int row_hi, int64_t* row_emit, int64_t* word_count, void* stream);
+int mgnns_exclusive_scan_i64(const int64_t* in, int64_t* out /* n+1 */, int n, void* stream);
+int mgnns_pmi_scatter_targets(const int32_t* tokens, int64_t D, int L, int V, int window, int pad_id,
+                              int row_lo, int row_hi, const int64_t* row_start, int64_t* cursor,
+                              int32_t* targets, void* stream);
+int mgnns_pmi_row_reduce(const int32_t* targets, const int64_t* row_start, int V, int min_count,
+                         int32_t* tmp_col, int32_t* tmp_cnt, int32_t* row_nnz, void* stream);
+int mgnns_pmi_compact(const int32_t* tmp_col, const int32_t* tmp_cnt, const int64_t* row_start,
+                      const int32_t* rowptr, int V, int32_t* col, int32_t* cnt, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Training-loop bookkeeping on the device.
+ *   mgnns_confusion_count: pred[b] = argmax_c scores[b,c]; conf[target[b]*C + pred[b]] += 1 (conf int32 [C,C],
+ *     accumulated, caller zeroes it); pred_out (optional) int64 [B].
+ *     ref: engine/Multi_GCN_Multihead_Att_engine.py:829-838 (argmax -> .cpu() -> sklearn accuracy/F1 every batch)
+ *   mgnns_label_cooccurrence: labels int32 [n_images, max_len] (lens int32 [n_images] valid entries per image):
+ *     nums[j] += images containing j, adj[a*C+b] += images containing both a and b, a != b (int64, accumulated).
+ *     ref: utils/util.py:336-357 (generate_nums, generate_Adj)
+ * ------------------------------------------------------------------------- */
+int mgnns_confusion_count(const float* scores, int64_t ld, const int64_t* target, int B, int C,
+                          int32_t* conf, int64_t* pred_out, void* stream);
+int mgnns_label_cooccurrence(const int32_t* labels, const int32_t* lens, int64_t n_images, int max_len,
+                             int C, int64_t* nums, int64_t* adj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

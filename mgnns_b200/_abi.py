@@ -47,6 +47,13 @@ SIGNATURES = {
     "mgnns_rowmax_f32": (c_int, [P, c_int64, c_int, P, P, P]),
     "mgnns_rowmax_bwd_f32": (c_int, [P, P, c_int64, c_int, P, P]),
     "mgnns_pmi_count": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P, P]),
+    "mgnns_pmi_row_emissions": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "mgnns_exclusive_scan_i64": (c_int, [P, P, c_int, P]),
+    "mgnns_pmi_scatter_targets": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "mgnns_pmi_row_reduce": (c_int, [P, P, c_int, c_int, P, P, P, P]),
+    "mgnns_pmi_compact": (c_int, [P, P, P, P, c_int, P, P, P]),
+    "mgnns_confusion_count": (c_int, [P, c_int64, P, c_int, c_int, P, P, P]),
+    "mgnns_label_cooccurrence": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),
     "mgnns_count_fill_csr_i32": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
     "mgnns_imgbank_fwd_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

@@ -278,7 +278,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
         key = (lens.data_ptr(), lens._version, tuple(lens.shape), int(max_text_len), dev)
         cache = self.__dict__.setdefault('_text_plans', {})
         hit = cache.get(key)
-        if hit is not None and hit[0]() is lens:
+        if hit is not None and hit[0]() is lens and (capacity is None or hit[1].capacity >= int(capacity)):
             return hit[1]
         import weakref
         plan = ops.LstmPlan(lens, max_text_len, dev, capacity)

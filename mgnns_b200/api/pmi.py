@@ -3,8 +3,10 @@
 Host work that stays on the host: reading the JSONL corpus, whitespace tokenisation, the
 vocabulary lookup (strings), and the float64 PMI arithmetic over the *non-zero* cells only (done
 with numpy in the reference's operation order so the pmi>0 edge set is identical).  The O(tokens x
-window) counting loop and the three O(V^2) Python loops of the reference are replaced by
-mgnns_pmi_count + an ordered CSR compaction on the device.
+window) counting loop and the three O(V^2) Python loops of the reference are replaced by the table-free
+device count (ops.pmi_count: row buckets + shared-memory column counters, csrc/pmi_sparse.cu), which
+emits the kept cells directly in the reference's row-major order.  `save_pmi` / `load_pmi` are the
+on-disk CSR form (.npz) of what the reference keeps as a dense int [V,V] array.
 """
 import json
 import os
@@ -13,49 +15,9 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..edge_map import SparseEdgeMap  # noqa: F401  (numpy-only class; this module is its reference-facing home)
 
 MAX_LEN = 100   # ref: utils/pmi.py:13-14 (texts are padded to 100 tokens, longer ones dropped)
-
-
-class SparseEdgeMap:
-    """CSR stand-in for the reference's dense int `edges_mappings[V,V]` (3.25 GB at V=20k).
-
-    Supports the two things the reference does with the matrix: `m[i, j]` lookups
-    (models/Text_GCN.py:160,:164) and `.shape`; `toarray()` densifies for small V.
-    Edge ids are 1 + CSR position (row-major enumeration, ref: utils/pmi.py:92-97); 0 = no edge.
-    """
-
-    def __init__(self, rowptr, col, n, eid=None):
-        self.rowptr = np.asarray(rowptr, dtype=np.int64)
-        self.col = np.asarray(col, dtype=np.int64)
-        self.eid = None if eid is None else np.asarray(eid, dtype=np.int64)
-        self.shape = (n, n)
-
-    @property
-    def nnz(self):
-        return int(self.col.shape[0])
-
-    def __getitem__(self, ij):
-        i, j = int(ij[0]), int(ij[1])
-        lo, hi = self.rowptr[i], self.rowptr[i + 1]
-        k = lo + np.searchsorted(self.col[lo:hi], j)
-        if k < hi and self.col[k] == j:
-            return int(k + 1) if self.eid is None else int(self.eid[k])
-        return 0
-
-    def toarray(self):
-        out = np.zeros(self.shape, dtype=np.int64)
-        rows = np.repeat(np.arange(self.shape[0]), np.diff(self.rowptr))
-        out[rows, self.col] = (np.arange(self.nnz) + 1) if self.eid is None else self.eid
-        return out
-
-    @classmethod
-    def from_dense(cls, m):
-        m = np.asarray(m)
-        rows, cols = np.nonzero(m)            # row-major order
-        rowptr = np.zeros(m.shape[0] + 1, dtype=np.int64)
-        np.add.at(rowptr, rows + 1, 1)
-        return cls(np.cumsum(rowptr), cols, m.shape[0], eid=m[rows, cols])
 
 
 def text_padding(content):
@@ -146,3 +108,20 @@ def cal_PMI(data_root_path, vocab_root_path, min_count, phase='train', window_si
     from .vocab import get_vocab_list
     vocab = get_vocab_list(data_root_path, vocab_root_path, min_count)
     return cal_PMI_from_texts(get_content(data_root_path), vocab, window_size, min_cooccurence)
+
+
+def save_pmi(path, edges_weights, edges_mappings, count):
+    """Persist cal_PMI's result as one compressed .npz of CSR arrays: a few MB instead of the
+    reference's dense int64 [V,V] `edges_mappings` (3.25 GB at V=20k, 20 GB at V=50k; ref: utils/pmi.py:89-105)."""
+    w = edges_weights.detach().cpu().numpy() if torch.is_tensor(edges_weights) else np.asarray(edges_weights)
+    if w.shape[0] != count:
+        raise ValueError("save_pmi: %d weights for count=%d" % (w.shape[0], count))
+    edges_mappings.save(path, weights=w)
+
+
+def load_pmi(path):
+    """-> (edges_weights FloatTensor[count,1], edges_mappings SparseEdgeMap, count), as cal_PMI returns them."""
+    m, w = SparseEdgeMap.load(path)
+    if w is None:
+        raise ValueError("load_pmi: %s holds no edge weights" % path)
+    return torch.Tensor(w), m, int(w.shape[0])

@@ -49,15 +49,33 @@ class GradientAllReducer:
         bid = len(self.buckets)
         for slot, p in enumerate(params):
             self.index[p] = (bid, slot)
-        self.buckets.append(dict(flat=flat, params=params, views=views, pending=len(params), work=None))
+        self.buckets.append(dict(flat=flat, params=params, views=views, pending=len(params), work=None,
+                                 events=[None] * len(params)))
 
     def _on_grad(self, p):
+        """Post-accumulate-grad hook.  With model.branch_streams the AccumulateGrad nodes of one bucket run on
+        different CUDA streams (the stream of each parameter's forward op), so every copy into the bucket records an
+        event on ITS stream, and the all-reduce — issued from whichever hook happens to complete the bucket — first
+        makes its launching stream wait on all of them; otherwise NCCL could read slots that are still being written."""
         bid, slot = self.index[p]
         b = self.buckets[bid]
         b['views'][slot].copy_(p.grad)
+        if p.is_cuda:
+            ev = b['events'][slot]
+            if ev is None:
+                ev = b['events'][slot] = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.device))
         b['pending'] -= 1
         if b['pending'] == 0 and self.world > 1:
-            b['work'] = dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._launch(b)
+
+    def _launch(self, b):
+        if b['flat'].is_cuda:
+            cur = torch.cuda.current_stream(b['flat'].device)
+            for ev in b['events']:
+                if ev is not None:
+                    cur.wait_event(ev)
+        b['work'] = dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     # -- call after loss.backward(), before clip_grad_norm_ ------------------------------------------
     def finish(self):
@@ -73,11 +91,16 @@ class GradientAllReducer:
                 if b['pending'] != 0:
                     # a parameter produced no gradient this step: reduce what is there
                     if self.world > 1:
-                        b['work'] = dist.all_reduce(b['flat'], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                        self._launch(b)
                 if b['work'] is not None:
                     b['work'].wait()
                     b['work'] = None
         for b in self.buckets:
+            if b['flat'].is_cuda:
+                cur = torch.cuda.current_stream(b['flat'].device)
+                for ev in b['events']:
+                    if ev is not None:
+                        cur.wait_event(ev)
             if self.world > 1:
                 b['flat'].div_(self.world)
             for v, p in zip(b['views'], b['params']):

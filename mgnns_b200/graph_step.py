@@ -24,7 +24,10 @@ class GraphedTrainStep:
         dev = batch['text'].device
         L = batch['text'].shape[1]
         n = int(batch['lens'].clamp(max=L).sum())
-        cap = plan_capacity if plan_capacity is not None else ((n + 1023) // 1024) * 1024
+        # Default capacity: this batch's token count with 12.5 % headroom, rounded up to 1024 rows (the LSTM's
+        # many-row products run over `capacity` rows, so B*L — the safe upper bound — would cost 6x on TumEmo-shaped
+        # text); a later batch with more tokens makes update_lengths() grow the plan and re-capture (see there).
+        cap = plan_capacity if plan_capacity is not None else min(batch['text'].shape[0] * L, ((n + n // 8 + 1023) // 1024) * 1024)
         self.lens_key = batch['lens']                      # identity of this tensor keys the plan cache
         self.plan = model.make_text_plan(self.lens_key, L, capacity=cap)
         self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -33,6 +36,14 @@ class GraphedTrainStep:
         self.graph_update = None
         self._flat = None
         self._views = None
+        self._warmup = warmup
+        self.recaptures = 0
+        self.time_allreduce = False
+        self.allreduce_events = []
+        self._capture(warmup)
+
+    def _capture(self, warmup):
+        dev = self.batch['text'].device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -111,12 +122,35 @@ class GraphedTrainStep:
         return loss
 
     def update_lengths(self, lens_cpu):
-        """New batch in the static buffers: refresh the LSTM schedule (tiny H2D on the current stream)."""
+        """New batch in the static buffers: refresh the LSTM schedule (tiny H2D on the CURRENT stream; the next
+        replay() must be ordered after that stream — LstmPlan.update_ documents the staging-buffer contract).
+        A batch with more valid tokens than the plan's capacity grows the plan by 1.5x and re-captures the step
+        (one-off cost of a few eager steps; `recaptures` counts them) instead of failing mid-training."""
+        L = self.batch['text'].shape[1]
+        n = int(lens_cpu.clamp(max=L).sum())
+        if n > self.plan.capacity:
+            cap = min(self.batch['text'].shape[0] * L, ((max(n, self.plan.capacity * 3 // 2) + 1023) // 1024) * 1024)
+            torch.cuda.synchronize()
+            self.lens_key.copy_(lens_cpu)                  # in-place: bumps the version, so the plan cache misses on purpose
+            self.plan = self.model.make_text_plan(self.lens_key, L, capacity=cap)
+            self._flat, self._views = None, None
+            for p in self.model.parameters():
+                p.grad = None
+            self.recaptures += 1
+            self._capture(max(1, self._warmup - 1))
+            return
         self.plan.update_(lens_cpu)
 
     def replay(self):
         self.graph.replay()
         if self.world > 1:
-            self._allreduce()
+            if self.time_allreduce:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._allreduce()
+                e1.record()
+                self.allreduce_events.append((e0, e1))
+            else:
+                self._allreduce()
             self.graph_update.replay()
         return self.loss

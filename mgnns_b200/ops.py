@@ -514,11 +514,14 @@ _gcn_fused_ws = _lib.mgnns_gcn_fused_workspace
 
 
 def gcn_fused_ok(x, weight) -> bool:
-    """Shapes / mode the fused layer kernel covers (forward only; callers that need gradients use spmm + mm)."""
+    """Shapes / mode the fused layer kernel covers (forward only; callers that need gradients use spmm + mm).
+    Opt-in (MGNNS_GCN_FUSED=1): measured on cfg 2 the fused kernel moves 1.0x the algorithmic HBM bytes (the
+    two-kernel path 2.1x) but is slower, because one 768-thread CTA per SM cannot keep as many neighbour-row loads
+    in flight as the stand-alone SpMM."""
     K, N = weight.shape
     return (_PRECISIONS[_precision] is not None and x.dim() == 3 and x.is_cuda and x.dtype is _f32
             and K % 4 == 0 and N % 32 == 0 and N <= 512 and K <= N and x.shape[2] == K
-            and os.environ.get("MGNNS_GCN_FUSED", "1") != "0")
+            and os.environ.get("MGNNS_GCN_FUSED", "0") == "1")
 
 
 def _gcn_fused_impl(x, weight, bias, tile_seg_ptr, segs, edges, tile_rows, tile_multi_ptr, multi_rows, n_tiles, n_rows,
@@ -703,9 +706,14 @@ def _attn_setup(ctx, inputs, output):
     u, bank, mask, scale, p_drop, seed = inputs
     ctx.save_for_backward(u, bank, mask, output[3])
     ctx.cfg = (scale, p_drop, seed)
+    ctx.set_materialize_grads(False)          # unused outputs arrive as None in backward (see the check there)
 
 
 def _attn_backward(ctx, g_ctx, g_attn, g_psum, g_lse):
+    if g_attn is not None or g_lse is not None:
+        # the attention weights / log-sum-exp are returned for inspection (the reference returns attn too, submodules.py:90)
+        # but no gradient formula flows through them here; a loss term built on them must fail loudly, not get zeros
+        raise NotImplementedError("mgnns::attn_q1: gradients through the returned attention weights / lse are not implemented")
     u, bank, mask, lse = ctx.saved_tensors
     scale, p_drop, seed = ctx.cfg
     u, bank, mask = _attn_check(u, bank, mask)
@@ -969,11 +977,13 @@ torch.library.register_autograd("mgnns::imgbank", _imgbank_backward, setup_conte
 
 
 # ----------------------------------------------------------------------------- PMI counting (no autograd)
-def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count: int):
+def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count: int, row_range=None):
     """tokens int32 [D,L] on CUDA -> (rowptr int32[V+1], col int32[nnz], cnt int32[nnz], word_count int64[V]).
 
-    Dense int32 [V,V] table in HBM (1.6 GB at V=20k, 10 GB at V=50k of the 180 GB), integer atomics,
-    then an ordered compaction to CSR keeping cells >= min_count.
+    No dense [V,V] table: the (centre -> target) pairs are bucketed by centre row and each row is counted in shared
+    memory (csrc/pmi_sparse.cu); memory is 12 bytes per emitted pair (35 M pairs = 0.4 GB for 200k TumEmo-shaped
+    documents, whatever V is).  `row_range=(lo, hi)` counts only centres in [lo, hi) — disjoint ranges on different
+    ranks partition the work with no reduction.  Two host syncs (total pairs, kept cells) size the buffers.
     """
     _need_cuda(tokens)
     if tokens.dtype != torch.int32 or tokens.dim() != 2:
@@ -981,8 +991,54 @@ def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count:
     tokens = tokens.contiguous()
     Dn, L = tokens.shape
     dev = tokens.device
+    lo, hi = (0, V) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    if not (0 <= lo <= hi <= V):
+        raise RuntimeError("mgnns pmi_count: bad row_range")
+    s = _stream()
+    i64 = torch.int64
+    row_emit = torch.empty((V,), device=dev, dtype=i64)
+    wc = torch.empty((V,), device=dev, dtype=i64)
+    _check(_lib.mgnns_pmi_row_emissions(tokens.data_ptr(), Dn, L, V, window, pad_id, lo, hi, row_emit.data_ptr(),
+                                        wc.data_ptr(), s), "pmi_row_emissions")
+    row_start = torch.empty((V + 1,), device=dev, dtype=i64)
+    _check(_lib.mgnns_exclusive_scan_i64(row_emit.data_ptr(), row_start.data_ptr(), V, s), "scan_i64")
+    total, biggest = (int(v) for v in torch.stack([row_start[-1], row_emit.max()]).tolist())     # host sync 1
+    if biggest >= 2 ** 31:
+        raise RuntimeError("mgnns pmi_count: a centre word has %d pairs; per-cell counts are int32 (< 2^31)" % biggest)
+    targets = torch.empty((max(total, 1),), device=dev, dtype=torch.int32)
+    cursor = torch.empty((V,), device=dev, dtype=i64)
+    _check(_lib.mgnns_pmi_scatter_targets(tokens.data_ptr(), Dn, L, V, window, pad_id, lo, hi, row_start.data_ptr(),
+                                          cursor.data_ptr(), targets.data_ptr(), s), "pmi_scatter_targets")
+    tmp_col = torch.empty((max(total, 1),), device=dev, dtype=torch.int32)
+    tmp_cnt = torch.empty((max(total, 1),), device=dev, dtype=torch.int32)
+    nnz_row = torch.empty((V,), device=dev, dtype=torch.int32)
+    with _timed("pmi_row_reduce"):
+        _check(_lib.mgnns_pmi_row_reduce(targets.data_ptr(), row_start.data_ptr(), V, min_count, tmp_col.data_ptr(),
+                                         tmp_cnt.data_ptr(), nnz_row.data_ptr(), s), "pmi_row_reduce")
+    rowptr = torch.empty((V + 1,), device=dev, dtype=torch.int32)
+    _check(_lib.mgnns_exclusive_scan_i32(nnz_row.data_ptr(), rowptr.data_ptr(), V, s), "scan")
+    nnz = int(rowptr[-1].item())                                                                # host sync 2
+    col = torch.empty((max(nnz, 1),), device=dev, dtype=torch.int32)[:nnz]
+    cnt = torch.empty((max(nnz, 1),), device=dev, dtype=torch.int32)[:nnz]
+    _check(_lib.mgnns_pmi_compact(tmp_col.data_ptr(), tmp_cnt.data_ptr(), row_start.data_ptr(), rowptr.data_ptr(), V,
+                                  col.data_ptr(), cnt.data_ptr(), s), "pmi_compact")
+    pmi_count.last_pairs = total
+    return rowptr, col, cnt, wc
+
+
+def pmi_count_dense(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count: int):
+    """Same result through a dense int32 [V,V] table in HBM (1.6 GB at V=20k) and an ordered compaction: the
+    round-1 path, kept for small vocabularies and as an independent cross-check of pmi_count (tests)."""
+    _need_cuda(tokens)
+    if tokens.dtype != torch.int32 or tokens.dim() != 2:
+        raise RuntimeError("mgnns pmi_count: tokens must be int32 [D,L]")
+    tokens = tokens.contiguous()
+    Dn, L = tokens.shape
+    dev = tokens.device
     if V * V * 4 > 120 * (1 << 30):
-        raise RuntimeError("mgnns pmi_count: V=%d needs a %.0f GB count table" % (V, V * V * 4 / 2**30))
+        raise RuntimeError("mgnns pmi_count_dense: V=%d needs a %.0f GB count table" % (V, V * V * 4 / 2**30))
+    if Dn * L * 2 * max(window, 1) >= 2 ** 31:
+        raise RuntimeError("mgnns pmi_count_dense: the corpus could overflow an int32 cell; use pmi_count")
     pair = torch.zeros((V, V), device=dev, dtype=torch.int32)
     wc = torch.zeros((V,), device=dev, dtype=torch.int64)
     s = _stream()
@@ -998,6 +1054,41 @@ def pmi_count(tokens: torch.Tensor, V: int, window: int, pad_id: int, min_count:
     _check(_lib.mgnns_count_fill_csr_i32(pair.data_ptr(), V, V, min_count, rowptr.data_ptr(), col.data_ptr(),
                                          cnt.data_ptr(), s), "count_fill_csr")
     return rowptr, col, cnt, wc
+
+
+# ----------------------------------------------------------------------------- loop bookkeeping (no autograd)
+def confusion_count(scores: torch.Tensor, target: torch.Tensor, conf: torch.Tensor, pred_out: Optional[torch.Tensor] = None):
+    """conf[target[b], argmax_c scores[b,c]] += 1 on the device (conf int32 [C,C], accumulated); optional pred_out
+    int64 [B].  Replaces the per-batch `.cpu()` + sklearn calls of the reference engine (engine:829-838)."""
+    _need_cuda(scores, target, conf, pred_out)
+    if scores.dim() != 2 or scores.dtype != torch.float32 or scores.stride(1) != 1:
+        raise RuntimeError("mgnns confusion_count: scores must be float32 [B,C] with unit column stride")
+    B, C = scores.shape
+    if target.dtype != torch.int64 or target.numel() != B or not target.is_contiguous():
+        raise RuntimeError("mgnns confusion_count: target must be contiguous int64 [B]")
+    if conf.dtype != torch.int32 or conf.numel() != C * C or not conf.is_contiguous():
+        raise RuntimeError("mgnns confusion_count: conf must be contiguous int32 [C,C]")
+    if pred_out is not None and (pred_out.dtype != torch.int64 or pred_out.numel() != B or not pred_out.is_contiguous()):
+        raise RuntimeError("mgnns confusion_count: pred_out must be contiguous int64 [B]")
+    _check(_lib.mgnns_confusion_count(scores.data_ptr(), scores.stride(0), target.data_ptr(), B, C, conf.data_ptr(),
+                                      _ptr(pred_out), _stream()), "confusion_count")
+    return conf
+
+
+def label_cooccurrence(labels: torch.Tensor, lens: torch.Tensor, C: int, nums: torch.Tensor, adj: torch.Tensor):
+    """nums[j] += images containing label j; adj[a,b] += images containing both (a != b) — int64, accumulated.
+    labels int32 [n_images, max_len], lens int32 [n_images].  (ref: utils/util.py:336-357)"""
+    _need_cuda(labels, lens, nums, adj)
+    if labels.dtype != torch.int32 or labels.dim() != 2 or not labels.is_contiguous():
+        raise RuntimeError("mgnns label_cooccurrence: labels must be contiguous int32 [n_images, max_len]")
+    if lens.dtype != torch.int32 or lens.numel() != labels.shape[0] or not lens.is_contiguous():
+        raise RuntimeError("mgnns label_cooccurrence: lens must be contiguous int32 [n_images]")
+    if nums.dtype != torch.int64 or nums.numel() != C or adj.dtype != torch.int64 or adj.numel() != C * C \
+            or not nums.is_contiguous() or not adj.is_contiguous():
+        raise RuntimeError("mgnns label_cooccurrence: nums / adj must be contiguous int64 [C] / [C,C]")
+    _check(_lib.mgnns_label_cooccurrence(labels.data_ptr(), lens.data_ptr(), labels.shape[0], labels.shape[1], C,
+                                         nums.data_ptr(), adj.data_ptr(), _stream()), "label_cooccurrence")
+    return nums, adj
 
 
 # ----------------------------------------------------------------------------- packed bi-LSTM recurrence
@@ -1064,13 +1155,25 @@ class LstmPlan:
         return packed, idx, n
 
     def update_(self, lens_cpu: torch.Tensor):
-        """Refresh the device tensors in place for a new batch (same B, L and capacity)."""
+        """Refresh the device tensors in place for a new batch (same B, L and capacity).
+
+        Stream contract: the two H2D copies are enqueued on the CURRENT stream from pinned staging buffers.  The
+        staging buffers are rewritten by the host on the next call, so this call first waits (host-side) for the
+        event recorded after the previous call's copies — a caller that runs `update_(k); replay(); update_(k+1)`
+        without any other synchronisation is safe.  Kernels that read the plan must be ordered after the stream
+        this was called on (GraphedTrainStep.update_lengths documents the same)."""
         packed, idx, n = self._host_arrays(lens_cpu, self.capacity)
         self.N = n
+        ev = self.__dict__.get('_staged')
+        if ev is not None:
+            ev.synchronize()                 # the previous update's H2D has finished reading the staging buffers
         self._host_plan.copy_(torch.from_numpy(packed))
         self._host_idx.copy_(torch.from_numpy(idx))
         self.plan.copy_(self._host_plan, non_blocking=True)
         self.idx.copy_(self._host_idx, non_blocking=True)
+        if self.plan.is_cuda:
+            self._staged = torch.cuda.Event()
+            self._staged.record(torch.cuda.current_stream(self.plan.device))
         return self
 
 

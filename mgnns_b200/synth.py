@@ -110,7 +110,7 @@ def synthetic_edge_map(V, seed=0, docs=2000, window=6, min_cooc=2, L=100):
     rows, cols = rows[keep], cols[keep]
     rowptr = np.zeros(V + 1, dtype=np.int64)
     np.add.at(rowptr, rows + 1, 1)
-    from .api.pmi import SparseEdgeMap
+    from .edge_map import SparseEdgeMap
     return SparseEdgeMap(np.cumsum(rowptr), cols, V), int(keep.sum()) + 1
 
 
@@ -183,3 +183,19 @@ def cfg2_word_graph(N=10000, mean_degree=64, seed=0):
     rows = np.repeat(np.arange(N), deg + 1)
     val = (1.0 / (deg + 1))[rows].astype(np.float32)
     return rowptr, cols, val
+
+
+def synthetic_label_graph(n, neighbours=8, seed=0):
+    """Co-occurrence statistics of an n-node label graph in the shape of the shipped pickles ({'adj','nums'},
+    ref: utils/util.py:359-380): every node co-occurs with `neighbours` random others (symmetrised, so ~2x that
+    per row).  With t = 0.04 every listed edge survives gen_A's threshold: Â has ~(2*neighbours+1)*n non-zeros
+    (0.4 % at n = 4096, the BASELINE cfg-5 label graphs)."""
+    rs = np.random.RandomState(seed)
+    nums = np.full(n, 1000.0)
+    adj = np.zeros((n, n))
+    rows = np.repeat(np.arange(n), neighbours)
+    cols = rs.randint(0, n, size=n * neighbours)
+    adj[rows, cols] = rs.randint(50, 500, size=n * neighbours)
+    adj = np.maximum(adj, adj.T)
+    np.fill_diagonal(adj, 0)
+    return {'adj': adj, 'nums': nums}

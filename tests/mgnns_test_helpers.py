@@ -64,7 +64,7 @@ def state_shapes(cfg=MODEL_CFG, edge_count=1):
     S['liner_img_object.weight'] = (d, 2048); S['liner_img_object.bias'] = (d,)
     S['liner_img_place.weight'] = (d, 2048); S['liner_img_place.bias'] = (d,)
     S['gc1.weight'] = (300, 1024); S['gc2.weight'] = (1024, 2048)
-    for kind, n in (('object', 80), ('place', 365)):
+    for kind, n in (('object', cfg.get('n_obj', 80)), ('place', cfg.get('n_plc', 365))):
         a = kind + '_attention.'
         S[a + 'w_q.weight'] = (300, 300); S[a + 'w_q.bias'] = (300,)
         S[a + 'w_k.weight'] = (300, n); S[a + 'w_k.bias'] = (300,)
@@ -83,7 +83,9 @@ def oracle_params(cfg=MODEL_CFG, edge_count=1, dtype=torch.float32):
     synth.fill_parameters(P, seed=cfg['seed'])
     P['embedding.weight'][0].zero_()
     from oracle import mgnns_oracle as O
-    for kind, n, t in (('object', 80, cfg['object_t']), ('place', 365, cfg['place_t'])):
-        a = synth.adj_dict(kind)
+    for kind, n, t, default in (('object', cfg.get('n_obj', 80), cfg['object_t'], 80),
+                                ('place', cfg.get('n_plc', 365), cfg['place_t'], 365)):
+        # shipped label graphs at the default sizes, synth.synthetic_label_graph otherwise (cfg 5)
+        a = synth.adj_dict(kind) if n == default else synth.synthetic_label_graph(n, seed=default)
         P[kind + '_A'] = torch.from_numpy(O.gen_A(n, t, a['adj'], a['nums'])).float()
     return {k: v.to(dtype) if v.dtype.is_floating_point else v for k, v in P.items()}

@@ -42,6 +42,67 @@ def test_reference_engine_and_entry_imports_unchanged_with_compat():
     assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/engine'), reason="reference checkout not present")
+def test_engine_hooks_feed_the_model_like_the_reference_engine():
+    """The reference's own GCNMultiClassEngine (imported unchanged through compat) and mgnns_b200.api.engine are
+    given the same Tumblr-shaped batch and a recording stub model on the CPU: both must hand the model the same seven
+    positional arguments (engine:825) and leave the same keys in `state` (engine:853-865, :826-838)."""
+    code = r"""
+import sys; sys.path.insert(0, %r)
+import mgnns_b200.compat as c; c.install(reference_root='/root/reference')
+import importlib, torch, numpy as np
+ref_eng = importlib.import_module('engine.Multi_GCN_Multihead_Att_engine')
+from mgnns_b200.api.engine import GCNMultiClassEngine as Ours
+from mgnns_b200 import synth
+B, V = 6, 50
+text, lens, mask = synth.make_texts(B, V, 100, seed=1)
+img = torch.randn(B, 3, 8, 8)
+oinp, pinp = synth.label_inputs(B)
+inp = (['id%%d' %% i for i in range(B)], ['t'] * B, text, lens, mask, img, ['p'] * B, oinp.contiguous(), pinp.contiguous())
+target = synth.make_labels(B, 7, seed=1)
+calls = []
+class Stub(torch.nn.Module):
+    def __init__(self):
+        super().__init__(); self.w = torch.nn.Parameter(torch.zeros(7))
+    def forward(self, *args):
+        calls.append(args)
+        g = torch.Generator().manual_seed(0)
+        return torch.randn(args[0].shape[0], 7, generator=g) + self.w
+model, crit = Stub(), torch.nn.CrossEntropyLoss()
+r = ref_eng.GCNMultiClassEngine({'use_gpu': False, 'fp16': False})
+r.state['input'], r.state['target'] = inp, target
+r.on_start_batch(False, model, crit, None)
+r.on_forward(False, model, crit, None)
+o = Ours({'use_gpu': False})
+o.state['input'], o.state['target'] = inp, target
+o.on_start_batch(False, model, crit, None)
+ours_args = o.model_args(torch.device('cpu'))
+ref_args = calls[0]
+assert len(ref_args) == len(ours_args) == 7
+for i, (a, b) in enumerate(zip(ref_args, ours_args)):
+    assert torch.equal(a.cpu(), b.cpu()) and (a.dtype == b.dtype), i
+for k in ('id', 'text_feature', 'text_lens', 'text_mask', 'object_feature', 'place_feature', 'image_name',
+          'object_input', 'place_input'):
+    assert (r.state[k] is o.state[k]) or r.state[k] == o.state[k], k
+assert r.state['object_feature'] is r.state['place_feature']          # the same image feeds both trunks
+# the reference's per-batch metrics equal ours computed from the confusion matrix of the same predictions
+from mgnns_b200.api.engine import metrics_from_confusion
+conf = np.zeros((7, 7)); np.add.at(conf, (target.numpy(), r.state['pred']), 1)
+acc, micro, macro, weighted = metrics_from_confusion(conf)
+assert abs(acc - r.state['acc']) < 1e-12 and abs(micro - r.state['micro_f1']) < 1e-12
+assert abs(macro - r.state['macro_f1']) < 1e-12 and abs(weighted - r.state['weighted_f1']) < 1e-12
+try:
+    o.on_forward(False, model, crit, None)
+except RuntimeError as e:
+    assert 'CUDA only' in str(e)
+else:
+    raise AssertionError('CPU on_forward must fail loudly')
+print('ok')
+""" % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), (out.stdout[-500:], out.stderr[-3000:])
+
+
 WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)

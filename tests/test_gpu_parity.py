@@ -204,11 +204,15 @@ def test_gcn_fused_matches_float64(ops, dev, n, K, N, batch, bias, act):
     gc.to(dev)
     x = rnd(batch, n, K, seed=N)
     slope = 0.2
-    assert ops.gcn_fused_ok(x.to(dev), gc.weight)
-    l0 = ops._abi.launch_count()
-    with torch.no_grad():
-        y = gc(x.to(dev), csr, act, slope)
-    assert ops._abi.launch_count() - l0 == 2             # weight split + the fused kernel, nothing else
+    os.environ['MGNNS_GCN_FUSED'] = '1'
+    try:
+        assert ops.gcn_fused_ok(x.to(dev), gc.weight)
+        l0 = ops._abi.launch_count()
+        with torch.no_grad():
+            y = gc(x.to(dev), csr, act, slope)
+        assert ops._abi.launch_count() - l0 == 2         # weight split + the fused kernel, nothing else
+    finally:
+        del os.environ['MGNNS_GCN_FUSED']
     ref = adj.double() @ x.double() @ gc.weight.detach().cpu().double()
     if bias:
         ref = ref + gc.bias.detach().cpu().double().view(1, 1, -1)
@@ -219,18 +223,16 @@ def test_gcn_fused_matches_float64(ops, dev, n, K, N, batch, bias, act):
     close(y, ref, 1e-4, 2e-5)
     # the unfused path (SpMM + dense layer) on the same inputs, and the autograd path, agree with it
     with torch.no_grad():
-        os.environ['MGNNS_GCN_FUSED'] = '0'
-        try:
-            y2 = gc(x.to(dev), csr, act, slope)
-        finally:
-            del os.environ['MGNNS_GCN_FUSED']
+        y2 = gc(x.to(dev), csr, act, slope)
     close(y2, ref, 1e-4, 2e-5)
     prev = ops.set_precision('tf32')
+    os.environ['MGNNS_GCN_FUSED'] = '1'
     try:
         with torch.no_grad():
             y3 = gc(x.to(dev), csr, act, slope)
     finally:
         ops.set_precision(prev)
+        del os.environ['MGNNS_GCN_FUSED']
     close(y3, ref, 2e-2, 5e-3)                           # plain TF32 operands: looser, stated bound
 
 
@@ -254,10 +256,10 @@ def test_cfg2_bench_shape_matches_oracle_float64(ops, dev):
     picks = (0, 1, 37, B - 1)
     refs = {b: torch.relu(O.graph_convolution(x[b].double(), A, w64)) for b in picks}
     with torch.no_grad():
-        y_fused = gc(xd, csr, ops.ACT_RELU)
-        os.environ['MGNNS_GCN_FUSED'] = '0'
+        y_two = gc(xd, csr, ops.ACT_RELU)
+        os.environ['MGNNS_GCN_FUSED'] = '1'
         try:
-            y_two = gc(xd, csr, ops.ACT_RELU)
+            y_fused = gc(xd, csr, ops.ACT_RELU)
         finally:
             del os.environ['MGNNS_GCN_FUSED']
     for b in picks:
@@ -725,6 +727,76 @@ def test_pmi_counts_large_synthetic_checksums(dev):
         expected += int((c & (tg >= 0)).sum())
     assert int(full[2].sum()) == expected
     assert int(full[3].sum()) == int(centre.sum())
+
+
+def _pair_keys_numpy(t, V, w, pad_id=0):
+    """Sorted (centre*V + target) keys with counts, straight from the definition (ref: utils/pmi.py:40-58)."""
+    L = t.shape[1]
+    centre = (t >= 0) & (t != pad_id)
+    keys = []
+    for off in range(-w, w):
+        if off == 0:
+            continue
+        c = t[:, max(0, -off):L - max(0, off)]
+        ok = centre[:, max(0, -off):L - max(0, off)]
+        tg = t[:, max(0, off):L + min(0, off)]
+        m = ok & (tg >= 0)
+        keys.append(c[m].astype(np.int64) * V + tg[m])
+    return np.unique(np.concatenate(keys), return_counts=True)
+
+
+@pytest.mark.parametrize("V,D,w,mc", [(977, 300, 6, 1), (977, 300, 3, 2), (60013, 400, 6, 1), (131, 50, 1, 1)])
+def test_pmi_sparse_count_bit_exact_vs_definition_and_dense_table(dev, V, D, w, mc):
+    """The table-free count (row buckets + shared-memory column counters) against the definition and against the
+    dense-table kernel; V=60,013 exceeds the 56k-word shared-memory chunk, so the column-chunk loop runs."""
+    from mgnns_b200 import ops
+    ids, lens, _ = synth.make_texts(D, V, 100, seed=V % 97, zipf_a=1.05)
+    tok = ids.to(torch.int32)
+    tok[ids == 1] = -1
+    tok[0, :] = 0                                   # an all-PAD document
+    tok[1, :] = 5                                   # one word repeated: a single heavy cell (5,5)
+    rowptr, col, cnt, wc = ops.pmi_count(tok.to(dev), V, w, 0, mc)
+    keys, kc = _pair_keys_numpy(tok.numpy(), V, w)
+    keep = kc >= mc
+    rows = np.repeat(np.arange(V), np.diff(rowptr.cpu().numpy().astype(np.int64)))
+    got = rows * V + col.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, keys[keep])          # row-major order, bit-exact cell set
+    assert np.array_equal(cnt.cpu().numpy(), kc[keep])
+    t = tok.numpy()
+    assert np.array_equal(wc.cpu().numpy(), np.bincount(t[t > 0], minlength=V))
+    if V < 5000:
+        d = ops.pmi_count_dense(tok.to(dev), V, w, 0, mc)
+        for a, b in zip((rowptr, col, cnt, wc), d):
+            assert torch.equal(a, b)
+
+
+def test_pmi_count_v50k_checksums_and_row_sharding(dev):
+    """cfg 5 vocabulary (V=50,000; the reference's dense table would be 20 GB): size-independent properties —
+    total of all cells = number of pairs in the corpus, word counts = live tokens, disjoint row ranges partition the
+    result exactly (how the count shards across ranks), and the CSR is row-major with strictly increasing columns."""
+    from mgnns_b200 import ops
+    V, D, L, w = 50000, 40000, 100, 6
+    ids, lens, _ = synth.make_texts(D, V, L, seed=11)
+    tok = ids.to(torch.int32).to(dev)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    rowptr, col, cnt, wc = ops.pmi_count(tok, V, w, 0, 1)
+    assert torch.cuda.max_memory_allocated() - base < 1 << 30          # < 1 GB of working memory at V=50k
+    keys, kc = _pair_keys_numpy(ids.numpy(), V, w)
+    assert int(cnt.sum()) == int(kc.sum()) == ops.pmi_count.last_pairs
+    assert col.numel() == keys.shape[0]
+    rp = rowptr.cpu().numpy().astype(np.int64)
+    rows = np.repeat(np.arange(V), np.diff(rp))
+    assert np.array_equal(rows * V + col.cpu().numpy().astype(np.int64), keys)
+    assert np.array_equal(cnt.cpu().numpy(), kc)
+    assert int(wc.sum()) == int((ids > 0).sum())
+    cut = 137
+    lo = ops.pmi_count(tok, V, w, 0, 1, row_range=(0, cut))
+    hi = ops.pmi_count(tok, V, w, 0, 1, row_range=(cut, V))
+    assert torch.equal(torch.cat([lo[1], hi[1]]), col) and torch.equal(torch.cat([lo[2], hi[2]]), cnt)
+    assert torch.equal(lo[0][:cut + 1], rowptr[:cut + 1]) and torch.equal(lo[3] + hi[3], wc)
+    two = ops.pmi_count(tok, V, w, 0, 2)
+    assert int(two[2].sum()) == int(kc[kc >= 2].sum()) and two[1].numel() == int((kc >= 2).sum())
 
 
 # ------------------------------------------------------------------------------------------- whole model
