@@ -139,6 +139,19 @@ int mgnns_attn_q1_bwd(const float* u, const float* bank, const float* mask, cons
                       int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
                       const uint64_t* seed_offset, float* grad_u, float* grad_bank, void* stream);
 
+/* The same two entry points on tensor-core fragments (mma.sync m16n8k8 TF32 with the 3xTF32 split: fp32-class accuracy;
+ * bank rows streamed through shared memory by bulk asynchronous copies).  Identical arguments and results;
+ * mgnns_attn_q1_tc_supported() says whether a shape is covered (H <= 16, D % 4 == 0, D <= 512, tables fit in shared
+ * memory) — callers use mgnns_attn_q1_fwd/bwd otherwise.  ref: models/submodules.py:106-119 */
+int mgnns_attn_q1_tc_supported(int H, int L, int D);
+int mgnns_attn_q1_tc_fwd(const float* u, const float* bank, const float* mask,
+                         int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                         const uint64_t* seed_offset, float* ctx, float* attn, float* psum, float* lse, void* stream);
+int mgnns_attn_q1_tc_bwd(const float* u, const float* bank, const float* mask, const float* lse,
+                         const float* grad_ctx, const float* grad_psum,
+                         int B, int H, int L, int D, float scale, float p_drop, uint64_t seed,
+                         const uint64_t* seed_offset, float* grad_u, float* grad_bank, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Label-query element-wise attention:
  *   out[b,c,h*dh+d] = dropout(softmax_d(Q[c,h,d]*K[b,h,d]*inv_scale))[d] * V[b,h,d]

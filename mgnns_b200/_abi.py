@@ -38,6 +38,11 @@ SIGNATURES = {
                                   P, P, P, P, P]),
     "mgnns_attn_q1_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                   P, P, P]),
+    "mgnns_attn_q1_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "mgnns_attn_q1_tc_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
+                                     P, P, P, P, P]),
+    "mgnns_attn_q1_tc_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
+                                     P, P, P]),
     "mgnns_label_attn_fwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,
                                      P, P]),
     "mgnns_label_attn_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_uint64, P,

@@ -120,9 +120,17 @@ __global__ void __launch_bounds__(PMI_REDUCE_THREADS) pmi_row_reduce_kernel(
             const int cw = min(chunk, V - c0);
             for (int i = tid; i < cw; i += PMI_REDUCE_THREADS) s_cnt[i] = 0;
             __syncthreads();
-            for (int64_t e = e0 + tid; e < e1; e += PMI_REDUCE_THREADS) {
-                const int t = __ldg(targets + e) - c0;
-                if (t >= 0 && t < cw) atomicAdd(&s_cnt[t], 1);
+            // four independent loads in flight per thread: the hub rows (millions of pairs) are latency bound otherwise
+            for (int64_t e = e0 + tid; e < e1; e += 4 * PMI_REDUCE_THREADS) {
+                int tv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t ee = e + (int64_t)q * PMI_REDUCE_THREADS;
+                    tv[q] = (ee < e1) ? __ldg(targets + ee) - c0 : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (tv[q] >= 0 && tv[q] < cw) atomicAdd(&s_cnt[tv[q]], 1);
             }
             __syncthreads();
             // ordered sweep: every thread owns a contiguous span (odd length: conflict-free strided reads)

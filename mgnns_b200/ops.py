@@ -677,18 +677,33 @@ def _attn_check(u, bank, mask):
     return u, bank, mask
 
 
+_attn_tc_cache = {}
+
+
+def attn_uses_tensor_cores(H, L, D) -> bool:
+    """True when the mma.sync (3xTF32) attention kernels cover the shape and MGNNS_ATTN is not 'scalar'."""
+    if os.environ.get("MGNNS_ATTN", "tc") == "scalar":
+        return False
+    key = (H, L, D)
+    v = _attn_tc_cache.get(key)
+    if v is None:
+        v = _attn_tc_cache[key] = bool(_lib.mgnns_attn_q1_tc_supported(H, L, D))
+    return v
+
+
 def _attn_impl(u, bank, mask, scale, p_drop, seed):
     u, bank, mask = _attn_check(u, bank, mask)
     B, H, D = u.shape
     L = bank.shape[1]
+    fwd = _lib.mgnns_attn_q1_tc_fwd if attn_uses_tensor_cores(H, L, D) else _lib.mgnns_attn_q1_fwd
     ctx = torch.empty((B, H, D), device=u.device, dtype=torch.float32)
     attn = torch.empty((H * B, 1, L), device=u.device, dtype=torch.float32)
     psum = torch.empty((B, H), device=u.device, dtype=torch.float32)
     lse = torch.empty((B, H), device=u.device, dtype=torch.float32)
     with _timed("attn_q1_fwd"):
-        _check(_lib.mgnns_attn_q1_fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale),
-                                      float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), ctx.data_ptr(), attn.data_ptr(),
-                                      psum.data_ptr(), lse.data_ptr(), _stream()), "attn_q1_fwd")
+        _check(fwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), B, H, L, D, float(scale),
+                   float(p_drop), seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), ctx.data_ptr(), attn.data_ptr(),
+                   psum.data_ptr(), lse.data_ptr(), _stream()), "attn_q1_fwd")
     return ctx, attn, psum, lse
 
 
@@ -723,10 +738,11 @@ def _attn_backward(ctx, g_ctx, g_attn, g_psum, g_lse):
     g_psum = None if g_psum is None else _f32c(g_psum, "grad_psum")
     gu = torch.empty_like(u)
     gbank = torch.empty_like(bank)
+    bwd = _lib.mgnns_attn_q1_tc_bwd if attn_uses_tensor_cores(H, L, D) else _lib.mgnns_attn_q1_bwd
     with _timed("attn_q1_bwd"):
-        _check(_lib.mgnns_attn_q1_bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
-                                      _ptr(g_psum), B, H, L, D, float(scale), float(p_drop),
-                                      seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), gu.data_ptr(), gbank.data_ptr(), _stream()),
+        _check(bwd(u.data_ptr(), bank.data_ptr(), _ptr(mask), lse.data_ptr(), g_ctx.data_ptr(),
+                   _ptr(g_psum), B, H, L, D, float(scale), float(p_drop),
+                   seed & 0xFFFFFFFFFFFFFFFF, _seed_ptr(), gu.data_ptr(), gbank.data_ptr(), _stream()),
                "attn_q1_bwd")
     return gu, gbank, None, None, None, None
 

@@ -390,9 +390,23 @@ def test_mha_layer_matches_reference_golden(dev, golden):
             close(p.grad, g, 1e-3, 1e-5, msg=n)
 
 
-@pytest.mark.parametrize("B,L,Hh,masked", [(7, 196, 4, False), (5, 100, 4, True), (3, 33, 16, True), (2, 1, 4, False)])
-def test_attn_q1_core_vs_dense_formula(dev, B, L, Hh, masked):
-    D = 300
+@pytest.fixture(params=['tc', 'scalar'])
+def attn_impl(request):
+    """Both attention implementations behind the one op: mma.sync fragments (default) and the CUDA-core kernels."""
+    prev = os.environ.get('MGNNS_ATTN')
+    os.environ['MGNNS_ATTN'] = request.param
+    yield request.param
+    if prev is None:
+        del os.environ['MGNNS_ATTN']
+    else:
+        os.environ['MGNNS_ATTN'] = prev
+
+
+@pytest.mark.parametrize("B,L,Hh,masked,D", [(7, 196, 4, False, 300), (5, 100, 4, True, 300), (3, 33, 16, True, 300),
+                                               (2, 1, 4, False, 300), (4, 70, 5, True, 300), (3, 65, 3, False, 64),
+                                               (2, 32, 8, True, 8), (3, 97, 12, False, 132)])
+def test_attn_q1_core_vs_dense_formula(dev, ops, attn_impl, B, L, Hh, masked, D):
+    assert ops.attn_uses_tensor_cores(Hh, L, D) == (attn_impl == 'tc')
     u, bank = rnd(B, Hh, D, seed=1, scale=0.2), rnd(B, L, D, seed=2)
     mask = None
     if masked:
@@ -418,7 +432,33 @@ def test_attn_q1_core_vs_dense_formula(dev, B, L, Hh, masked):
     close(bg.grad, bd.grad, 1e-3, 1e-5)
 
 
-def test_attention_dropout_statistics_and_determinism(dev):
+def test_attn_q1_masked_rows_inside_the_sequence_and_zero_gradient_rows(dev, attn_impl):
+    """Interior masked rows (not only a padded tail), an all-but-one-masked sample, and rows past the last live chunk:
+    their probabilities and bank gradients are exactly zero."""
+    B, L, Hh, D = 4, 100, 4, 300
+    u, bank = rnd(B, Hh, D, seed=11, scale=0.2), rnd(B, L, D, seed=12)
+    mask = torch.ones(B, L)
+    mask[0, 3:40] = 0
+    mask[0, 77:] = 0
+    mask[1, 1:] = 0
+    mask[2, :50] = 0
+    ud, bd = u.double().requires_grad_(), bank.double().requires_grad_()
+    s = (torch.einsum('bhd,bld->bhl', ud, bd) * 0.1).masked_fill(mask.unsqueeze(1) == 0, float('-inf'))
+    p = torch.softmax(s, -1)
+    r = rnd(B, Hh, D, seed=13).double()
+    (torch.einsum('bhl,bld->bhd', p, bd) * r).sum().backward()
+    ug, bg = u.to(dev).requires_grad_(), bank.to(dev).requires_grad_()
+    ctx, attn, psum, lse = torch.ops.mgnns.attn_q1(ug, bg, mask.to(dev), 0.1, 0.0, 0)
+    close(ctx, torch.einsum('bhl,bld->bhd', p, bd), 1e-4, 1e-5)
+    a = attn.view(Hh, B, L).permute(1, 0, 2).cpu()
+    assert (a[mask.unsqueeze(1).expand(B, Hh, L) == 0] == 0).all()
+    (ctx * r.float().to(dev)).sum().backward()
+    close(ug.grad, ud.grad, 1e-3, 1e-5)
+    close(bg.grad, bd.grad, 1e-3, 1e-5)
+    assert (bg.grad.cpu()[mask == 0] == 0).all()
+
+
+def test_attention_dropout_statistics_and_determinism(dev, attn_impl):
     B, L, Hh, D = 64, 100, 4, 300
     u, bank = rnd(B, Hh, D, seed=1, scale=0.05).to(dev), rnd(B, L, D, seed=2).to(dev)
     _, attn0, _, _ = torch.ops.mgnns.attn_q1(u, bank, None, 0.1, 0.0, 0)
