@@ -88,6 +88,22 @@ int mgnns_spmm_csr_f32(int n_rows, const int32_t* rowptr, const int32_t* col, co
                        float* Y, int64_t ldy, int64_t strideY,
                        int F, int batch, void* stream);
 
+/* The same product for batched features on a big graph, with the hub neighbour rows staged in shared memory
+ * (persistent 1024-thread CTAs; a work item = (sample, chunk of row segments); the `n_hub` most referenced columns of
+ * X[b] live in a shared-memory table that is reloaded only when the sample changes).  The matrix comes as a host-built
+ * plan (mgnns_b200.api.graph_util.hub_plan_arrays):
+ *   hub_cols      int32 [n_hub]            column staged in each table slot (n_hub <= mgnns_spmm_hub_capacity(F))
+ *   chunk_seg_ptr int32 [n_chunks + 1]     segment range of a chunk
+ *   segs          int32 [n_segs, 4]        {first edge, hub edges, edges, row | 1<<31 if the row's only segment}
+ *   edges         int32 [nnz, 2]           hub edges first within a row: {byte offset in the table | in X[b], bits of val}
+ *   multi_rows    int32 [n_multi]          rows spanning several segments (zeroed first, then accumulated atomically)
+ * ref: torch.matmul(adj, support) models/Multi_GCN_Multihead_att.py:54 at BASELINE.json configs[1] size */
+int mgnns_spmm_hub_capacity(int F);
+int mgnns_spmm_hub_f32(const float* X, int64_t ldx, int64_t strideX, float* Y, int64_t ldy, int64_t strideY,
+                       int F, int batch, const int32_t* hub_cols, int n_hub,
+                       const int32_t* chunk_seg_ptr, int n_chunks, const int32_t* segs, const int32_t* edges,
+                       const int32_t* multi_rows, int n_multi, void* stream);
+
 /* dense [n,n] fp32 adjacency -> CSR (entries != 0), three steps so the caller
  * can allocate col/val after reading nnz = rowptr[n]                        */
 int mgnns_dense_row_nnz_f32(const float* A, int n_rows, int n_cols, int64_t ld, int32_t* row_nnz, void* stream);

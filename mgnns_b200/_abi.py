@@ -27,6 +27,9 @@ SIGNATURES = {
     "mgnns_act_bwd_f32": (c_int, [P, P, P, c_int64, c_int, c_float, P]),
     "mgnns_colsum_f32": (c_int, [P, c_int64, c_int, c_int64, P, P]),
     "mgnns_spmm_csr_f32": (c_int, [c_int, P, P, P, P, c_int64, c_int64, P, c_int64, c_int64, c_int, c_int, P]),
+    "mgnns_spmm_hub_capacity": (c_int, [c_int]),
+    "mgnns_spmm_hub_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int64, c_int, c_int, P, c_int, P, c_int, P, P, P,
+                                   c_int, P]),
     "mgnns_dense_row_nnz_f32": (c_int, [P, c_int, c_int, c_int64, P, P]),
     "mgnns_exclusive_scan_i32": (c_int, [P, P, c_int, P]),
     "mgnns_dense_fill_csr_f32": (c_int, [P, c_int, c_int, c_int64, P, P, P, P]),

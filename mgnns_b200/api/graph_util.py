@@ -151,6 +151,74 @@ def fused_plan_arrays(rowptr, col, val, ldx, tile_rows=FUSED_TILE_ROWS, seg_edge
                 tile_multi_ptr=tile_multi_ptr, multi_rows=multi_rows, n_tiles=n_tiles, n_rows=n)
 
 
+def hub_plan_arrays(rowptr, col, val, n_cols, ldx, F, hub_capacity, n_chunks, seg_edges=FUSED_SEG_EDGES):
+    """Host arrays of the hub-staged SpMM plan (see csrc/spmm_hub.cu, mgnns_spmm_hub_f32).
+
+    The `hub_capacity` most referenced columns become the shared-memory hub table (slot s holds X[b, hub_cols[s], :]).
+    Every row's edges are reordered hub-first and re-indexed (hub edge: byte offset of its slot in the table, other
+    edge: byte offset of its column's row in X[b]); rows are cut into segments of at most `seg_edges` edges; segments
+    are dealt, in row order, to `n_chunks` chunks of about equal edge count and sorted longest-first inside a chunk
+    (the kernel's warps take them round-robin)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int64)
+    val = np.ascontiguousarray(np.asarray(val, dtype=np.float32))
+    n = rowptr.shape[0] - 1
+    nnz = col.shape[0]
+    if max(n_cols * ldx, hub_capacity * F) * 4 >= 2 ** 32:
+        raise ValueError("hub SpMM plan: byte offsets do not fit 32 bits")
+    deg = np.diff(rowptr)
+    coldeg = np.bincount(col, minlength=n_cols)
+    hub_cols = np.argsort(-coldeg, kind='stable')[:max(0, min(hub_capacity, n_cols))]
+    hub_cols = hub_cols[coldeg[hub_cols] > 1]                          # a column used once gains nothing from staging
+    slot = np.full(n_cols, -1, dtype=np.int64)
+    slot[hub_cols] = np.arange(hub_cols.shape[0])
+    is_hub = slot[col] >= 0
+    rows = np.repeat(np.arange(n), deg)
+    order = np.lexsort((np.arange(nnz), ~is_hub, rows))                # by row, hub edges first, original order kept
+    col2, val2, hub2 = col[order], val[order], is_hub[order]
+    edges = np.empty((nnz, 2), dtype=np.int32)
+    edges[:, 0] = np.where(hub2, slot[col2] * F * 4, col2 * ldx * 4).astype(np.uint32).view(np.int32)
+    edges[:, 1] = val2.view(np.int32)
+    hub_per_row = np.bincount(rows, weights=is_hub, minlength=n).astype(np.int64)
+    n_seg = np.maximum(1, (deg + seg_edges - 1) // seg_edges)
+    total = int(n_seg.sum())
+    owner = np.repeat(np.arange(n), n_seg)
+    first = np.cumsum(n_seg) - n_seg
+    j = np.arange(total) - np.repeat(first, n_seg)
+    seg_len = np.minimum(seg_edges, deg[owner] - j * seg_edges).clip(min=0)
+    seg_hub = np.clip(hub_per_row[owner] - j * seg_edges, 0, seg_len)
+    seg_beg = rowptr[owner] + j * seg_edges
+    sole = n_seg[owner] == 1
+    # contiguous chunks of about equal edge count (every segment costs at least one unit so empty rows spread too)
+    n_chunks = max(1, min(n_chunks, total))
+    cost = np.cumsum(np.maximum(seg_len, 1))
+    chunk_of = np.minimum(n_chunks - 1, (cost - 1) * n_chunks // cost[-1])
+    key = np.lexsort((-seg_len, chunk_of))
+    roww = (owner[key] | np.where(sole[key], 1 << 31, 0)).astype(np.uint32).view(np.int32)
+    segs = np.stack([seg_beg[key].astype(np.int32), seg_hub[key].astype(np.int32), seg_len[key].astype(np.int32), roww], axis=1)
+    chunk_seg_ptr = np.zeros(n_chunks + 1, dtype=np.int64)
+    np.add.at(chunk_seg_ptr, chunk_of + 1, 1)
+    chunk_seg_ptr = np.cumsum(chunk_seg_ptr).astype(np.int32)
+    multi_rows = np.nonzero(n_seg > 1)[0].astype(np.int32)
+    return dict(hub_cols=hub_cols.astype(np.int32), chunk_seg_ptr=chunk_seg_ptr, segs=np.ascontiguousarray(segs),
+                edges=edges, multi_rows=multi_rows, n_chunks=n_chunks, n_rows=n,
+                hub_edge_fraction=float(is_hub.mean()) if nnz else 0.0)
+
+
+class HubSpmmPlan:
+    """Device copy of hub_plan_arrays()."""
+
+    def __init__(self, arrays, ldx, F, device):
+        self.ldx, self.F, self.n_chunks, self.n_rows = ldx, F, arrays['n_chunks'], arrays['n_rows']
+        self.hub_edge_fraction = arrays['hub_edge_fraction']
+        self.n_hub, self.n_multi = int(arrays['hub_cols'].shape[0]), int(arrays['multi_rows'].shape[0])
+        for k in ('hub_cols', 'chunk_seg_ptr', 'segs', 'edges', 'multi_rows'):
+            a = arrays[k]
+            if a.size == 0:
+                a = np.zeros((1,) + a.shape[1:], dtype=np.int32)
+            setattr(self, k, torch.from_numpy(np.ascontiguousarray(a)).to(device))
+
+
 class FusedGcnPlan:
     """Device copy of fused_plan_arrays()."""
 

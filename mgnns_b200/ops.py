@@ -449,6 +449,28 @@ _LIB.define("spmm_csr(Tensor rowptr, Tensor col, Tensor val, Tensor x, Tensor t_
             "Tensor t_val, int n_rows) -> Tensor")
 
 
+_HUB_MIN_BATCH = int(os.environ.get("MGNNS_SPMM_HUB_MIN_BATCH", "16"))
+_HUB_MIN_NNZ = int(os.environ.get("MGNNS_SPMM_HUB_MIN_NNZ", "100000"))
+_hub_plans = {}
+
+
+def _hub_plan(rowptr, col, val, n_rows, n_cols, F):
+    """Execution plan of a CSR matrix for mgnns_spmm_hub_f32, built on the host once per (matrix, feature width) —
+    one device->host copy of the CSR arrays — and cached on the identity and version of the three tensors."""
+    key = (rowptr.data_ptr(), col.data_ptr(), val.data_ptr(), rowptr._version, col._version, val._version, n_cols, F)
+    plan = _hub_plans.get(key)
+    if plan is None:
+        from .api.graph_util import HubSpmmPlan, hub_plan_arrays
+        sms = torch.cuda.get_device_properties(x_dev := rowptr.device).multi_processor_count
+        arrays = hub_plan_arrays(rowptr.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy(), n_cols, F, F,
+                                 int(_lib.mgnns_spmm_hub_capacity(F)), sms, seg_edges=64)
+        plan = HubSpmmPlan(arrays, F, F, x_dev)
+        if len(_hub_plans) > 16:
+            _hub_plans.clear()
+        _hub_plans[key] = plan
+    return plan
+
+
 def _spmm_raw(rowptr, col, val, x, n_rows):
     _need_cuda(rowptr, col, val, x)
     x = _f32c(x, "x")
@@ -464,6 +486,16 @@ def _spmm_raw(rowptr, col, val, x, n_rows):
         raise RuntimeError("mgnns::spmm_csr: CSR arrays must be int32/int32/float32")
     if rowptr.numel() != n_rows + 1:
         raise RuntimeError("mgnns::spmm_csr: rowptr has %d entries, expected %d" % (rowptr.numel(), n_rows + 1))
+    if (batch >= _HUB_MIN_BATCH and col.numel() >= _HUB_MIN_NNZ and F % 4 == 0 and F <= 512
+            and x.data_ptr() % 16 == 0 and os.environ.get("MGNNS_SPMM_HUB", "1") != "0"):
+        # batched features on a big graph: persistent kernel with the hub neighbour rows staged in shared memory
+        plan = _hub_plan(rowptr, col, val, n_rows, n_cols, F)
+        with _timed("spmm_hub"):
+            _check(_lib.mgnns_spmm_hub_f32(x.data_ptr(), F, n_cols * F, y.data_ptr(), F, n_rows * F, F, batch,
+                                           plan.hub_cols.data_ptr(), plan.n_hub, plan.chunk_seg_ptr.data_ptr(), plan.n_chunks,
+                                           plan.segs.data_ptr(), plan.edges.data_ptr(), plan.multi_rows.data_ptr(),
+                                           plan.n_multi, _stream()), "spmm_hub")
+        return y
     for b0 in range(0, batch, 65535):
         nb = min(65535, batch - b0)
         with _timed("spmm_csr"):

@@ -32,11 +32,11 @@ ref = torch.relu(A @ x[B - 1].double().cpu() @ gc.weight.detach().double().cpu()
 alg_bytes = 4 * (B * N * Fin + B * N * Fout + Fin * Fout) + 8 * nnz + 4 * (N + 1)
 print("cfg2: N=%d nnz=%d B=%d  algorithmic bytes %.3f GB, gather bytes %.1f GB" % (N, nnz, B, alg_bytes / 1e9, 4.0 * nnz * B * Fin / 1e9), flush=True)
 
-for fused in ('1', '0'):
+for fused in ('0', '1'):
     os.environ['MGNNS_GCN_FUSED'] = fused
     for mode in ('tf32x3', 'tf32'):
         ops.set_precision(mode)
-        names = ['gcn_fused'] if fused == '1' else ['spmm_csr', 'linear_tc']
+        names = ['gcn_fused'] if fused == '1' else ['spmm_hub', 'spmm_csr', 'linear_tc']
         with torch.no_grad():
             for _ in range(2):
                 y = gc(x, csr, ops.ACT_RELU)
@@ -50,7 +50,7 @@ for fused in ('1', '0'):
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        parts = "  ".join("%s %.3f ms" % (n, ops.KernelTimers.mean_ms(n)[0] or float('nan')) for n in names)
+        parts = "  ".join("%s %.3f ms" % (n, ops.KernelTimers.mean_ms(n)[0]) for n in names if ops.KernelTimers.mean_ms(n)[0])
         ops.KernelTimers.reset([])
         print("fused=%s mode=%s: total %.3f ms (%.0f GB/s algorithmic = %.3f of 6535.7)  %s  max|err| %.2e (ref rms %.3f)"
               % (fused, mode, ms, alg_bytes / ms / 1e6, alg_bytes / ms / 1e6 / 6535.7, parts, err, ref.pow(2).mean().sqrt().item()),

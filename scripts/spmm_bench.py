@@ -29,6 +29,7 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
+print('hub kernel' if os.environ.get('MGNNS_SPMM_HUB', '1') != '0' else 'plain kernel')
 nnz = cols.shape[0]
 print("B=%d: %.3f ms  gather %.1f TB/s  hbm-algorithmic %.0f GB/s  max|err| %.1e"
       % (B, ms, nnz * B * F * 4 / ms / 1e9, 8.0 * B * N * F / ms / 1e6, err))

@@ -87,3 +87,40 @@ def test_cfg2_word_graph_has_the_specified_size():
     assert (np.diff(col)[same_row] > 0).all()                              # sorted, no duplicates
     np.testing.assert_allclose(np.add.reduceat(val, rowptr[:-1]), 1.0, rtol=1e-5)
     assert deg.max() > 10 * np.median(deg)                                 # heavy tail
+
+
+def test_hub_spmm_plan_reproduces_spmm_and_stages_the_hubs():
+    """Emulate mgnns_spmm_hub_f32's walk over the plan (chunk -> segment -> hub edges from the table, other edges from
+    X) in float64 and compare with the dense product."""
+    from mgnns_b200.api.graph_util import hub_plan_arrays
+    n, F, ldx = 900, 8, 12
+    rowptr, col, val = synth.cfg2_word_graph(n, 40, seed=5)
+    plan = hub_plan_arrays(rowptr, col, val, n, ldx, F, hub_capacity=25, n_chunks=7, seg_edges=64)
+    rs = np.random.RandomState(2)
+    x = rs.randn(n, ldx)
+    table = x[plan['hub_cols'], :F]
+    y = np.zeros((n, F))
+    written = np.zeros(n, dtype=np.int64)
+    for ch in range(plan['n_chunks']):
+        seg = plan['segs'][plan['chunk_seg_ptr'][ch]:plan['chunk_seg_ptr'][ch + 1]]
+        assert (np.diff(seg[:, 2]) <= 0).all()                      # longest first
+        for beg, n_hub, cnt, roww in seg:
+            row, sole = int(roww) & 0x7fffffff, int(roww) < 0
+            assert 0 <= n_hub <= cnt <= 64
+            e = plan['edges'][beg:beg + cnt]
+            off = e[:, 0].view(np.uint32).astype(np.int64)
+            w = e[:, 1].copy().view(np.float32).astype(np.float64)
+            acc = w[:n_hub] @ table[off[:n_hub] // (F * 4)] if n_hub else 0.0
+            acc = acc + (w[n_hub:] @ x[off[n_hub:] // (ldx * 4), :F] if cnt > n_hub else 0.0)
+            y[row] += acc
+            written[row] += 1
+            assert sole == (np.diff(rowptr)[row] <= 64)
+    assert set(np.nonzero(written > 1)[0].tolist()) == set(plan['multi_rows'].tolist())
+    dense = np.zeros((n, n))
+    dense[np.repeat(np.arange(n), np.diff(rowptr)), col] = val
+    np.testing.assert_allclose(y, dense @ x[:, :F], rtol=1e-10, atol=1e-12)
+    coldeg = np.bincount(col, minlength=n)
+    assert coldeg[plan['hub_cols']].min() >= np.sort(coldeg)[-25]   # the most referenced columns are the staged ones
+    assert 0.1 < plan['hub_edge_fraction'] < 1.0
+    per_chunk = np.array([plan['segs'][plan['chunk_seg_ptr'][c]:plan['chunk_seg_ptr'][c + 1], 2].sum() for c in range(7)])
+    assert per_chunk.max() < 1.3 * per_chunk.mean()

@@ -136,6 +136,43 @@ def test_spmm_matches_dense(dev, n, F, batch):
     close(xg.grad, torch.matmul(adj.double().t(), r.double()), 1e-5, 1e-5)
 
 
+@pytest.mark.parametrize("n,F,batch,density", [(3000, 300, 20, 0.04), (2500, 64, 17, 0.08), (2048, 132, 33, 0.06)])
+def test_spmm_hub_staged_kernel_matches_dense_and_plain_kernel(ops, dev, n, F, batch, density):
+    """The persistent SpMM with shared-memory hub rows (batched features, nnz >= 100k): hub columns, a 1,500-edge hub
+    ROW (segments combined with vector atomics), an empty row; forward and the transpose product of the backward,
+    against float64 and against the plain kernel (MGNNS_SPMM_HUB=0)."""
+    from mgnns_b200.api.graph_util import CSRAdjacency
+    adj = random_adj(n, n, density, seed=n)
+    g = torch.Generator().manual_seed(n + 7)
+    adj[:, 5] = torch.randn(n, generator=g)
+    adj[:, 17] = torch.randn(n, generator=g)
+    adj[9, :1500] = torch.randn(1500, generator=g)
+    adj[3] = 0
+    adj = adj / adj.abs().sum(1, keepdim=True).clamp(min=1.0)
+    rowptr, cols, val = _csr_host(adj)
+    assert cols.shape[0] >= 100000
+    csr = CSRAdjacency.from_scipy_like(rowptr, cols, val, n, dev)
+    x = rnd(batch, n, F, seed=F)
+    xg = x.to(dev).requires_grad_()
+    ops.KernelTimers.reset(['spmm_hub', 'spmm_csr'])
+    y = csr.spmm(xg)
+    r = rnd(*y.shape, seed=1)
+    (y * r.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert ops.KernelTimers.mean_ms('spmm_hub')[1] == 2 and ops.KernelTimers.mean_ms('spmm_csr')[1] == 0
+    ops.KernelTimers.reset([])
+    close(y, torch.matmul(adj.double(), x.double()), 1e-5, 1e-5)
+    close(xg.grad, torch.matmul(adj.double().t(), r.double()), 1e-5, 1e-5)
+    assert (y[:, 3] == 0).all()
+    os.environ['MGNNS_SPMM_HUB'] = '0'
+    try:
+        with torch.no_grad():
+            y0 = csr.spmm(x.to(dev))
+    finally:
+        del os.environ['MGNNS_SPMM_HUB']
+    assert (y - y0).abs().max().item() < 1e-5
+
+
 def test_dense_to_csr_ordering_and_scan(ops, dev):
     adj = random_adj(3000, 517, 0.02, seed=5)
     rowptr, col, val = ops.dense_to_csr(adj.to(dev))
