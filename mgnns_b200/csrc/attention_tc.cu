@@ -112,7 +112,10 @@ __device__ __forceinline__ int tca_live_rows(const float* mk, int L, unsigned ch
 
 // score partials of one chunk: warp = (row tile mt of 16 rows, K quarter ks); NTT head tiles of 8 columns whose query
 // rows come from q0 (tiles < NT) or q1 (tiles >= NT, backward only)
-template <int NT, int NTT>
+// PACK (H <= 4, one head tile per query table): the table's eight rows are [hi(q_0..3) | lo(q_0..3)], already exact
+// TF32 splits, so one pair of MMAs (A_hi, A_lo) yields A.q_hi in columns 0-3 and A.q_lo in columns 4-7 — two MMAs
+// and no B-side split instead of three MMAs and four split operations; the caller adds column h and h+4.
+template <int NT, int NTT, bool PACK>
 __device__ __forceinline__ void tca_score_partials(const float* __restrict__ cb, const float* __restrict__ q0,
                                                    const float* __restrict__ q1, float* __restrict__ part,
                                                    const TcaDims& dm, int warp, int lane) {
@@ -138,10 +141,17 @@ __device__ __forceinline__ void tca_score_partials(const float* __restrict__ cb,
         for (int i = 0; i < 4; ++i) tca_split(a[i], ah[i], al[i]);
 #pragma unroll
         for (int j = 0; j < NTT; ++j) {
-            const int hr = (j < NT ? j : j - NT) * 8 + g;
-            const float* qp = (j < NT ? q0 : q1) + hr * dm.DU + k0;
-            const bool on = hr < dm.HR;
-            tca_mma3_pre(c[j], ah, al, on ? qp[0] : 0.f, on ? qp[4] : 0.f);
+            if (PACK) {
+                const float* qp = (j < NT ? q0 : q1) + g * dm.DU + k0;
+                const uint32_t b0 = __float_as_uint(qp[0]), b1 = __float_as_uint(qp[4]);
+                tca_mma(c[j], ah, b0, b1);
+                tca_mma(c[j], al, b0, b1);
+            } else {
+                const int hr = (j < NT ? j : j - NT) * 8 + g;
+                const float* qp = (j < NT ? q0 : q1) + hr * dm.DU + k0;
+                const bool on = hr < dm.HR;
+                tca_mma3_pre(c[j], ah, al, on ? qp[0] : 0.f, on ? qp[4] : 0.f);
+            }
         }
     }
     constexpr int NC = 8 * NTT;
@@ -155,7 +165,7 @@ __device__ __forceinline__ void tca_score_partials(const float* __restrict__ cb,
 
 // acc^T[feature tile][head tile] += chunk^T . W for the warp's feature tiles; W[r][h] row-major with stride ws
 // (forward: softmax weights of the chunk) or column-major tables T[h][row] with stride ws (backward: dS), COLMAJOR
-template <int NT, bool COLMAJOR>
+template <int NT, bool COLMAJOR, bool PACK>
 __device__ __forceinline__ void tca_accumulate_t(const float* __restrict__ cb, const float* __restrict__ w, int ws,
                                                  float (&acc)[3][NT][4], const TcaDims& dm, int warp, int lane) {
     const int g = lane >> 2, t = lane & 3;
@@ -186,14 +196,20 @@ __device__ __forceinline__ void tca_accumulate_t(const float* __restrict__ cb, c
                     const float* wp = w + r0 * ws + j * 8 + g;
                     b0 = wp[0]; b1 = wp[4 * ws];
                 }
-                tca_mma3_pre(acc[i][j], ah, al, b0, b1);
+                if (PACK) {                              // columns are [hi | lo] of the weights: no split, two MMAs
+                    tca_mma(acc[i][j], ah, __float_as_uint(b0), __float_as_uint(b1));
+                    tca_mma(acc[i][j], al, __float_as_uint(b0), __float_as_uint(b1));
+                } else {
+                    tca_mma3_pre(acc[i][j], ah, al, b0, b1);
+                }
             }
         }
     }
 }
 
 // =====================================================================================================================
-template <int NT, bool MASKED, bool DROPOUT>
+// PACK: H <= 4 — query table and chunk weights carry [hi | lo] in the eight fragment columns (see tca_score_partials)
+template <int NT, bool MASKED, bool DROPOUT, bool PACK>
 __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
     const float* __restrict__ u, const float* __restrict__ bank, const float* __restrict__ mask, TcaDims dm,
     float scale, float p_drop, uint64_t seed, const uint64_t* seed_offset,
@@ -202,8 +218,9 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
     extern __shared__ __align__(16) float sm[];
     const int CH = TCA_R * dm.D + TCA_PAD;
     float* chunk = sm;                                   // [2][CH]
-    float* us = chunk + 2 * CH;                          // [HR][DU]
-    float* part = us + dm.HR * dm.DU;                    // [4][R][NC]
+    const int UR = PACK ? 8 : dm.HR;                     // rows of the query table
+    float* us = chunk + 2 * CH;                          // [UR][DU]
+    float* part = us + UR * dm.DU;                       // [4][R][NC]
     float* pw = part + TCA_KSPLIT * TCA_R * NC;          // [R][NC] softmax weights of the chunk
     float* sc = pw + TCA_R * NC;                         // [HR][LT] scaled scores (for the returned attention weights)
     float* stat = sc + dm.HR * dm.LT;                    // corr[NC], M[NC], S[NC]
@@ -225,9 +242,17 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 2 * CH; i += TCA_THREADS) chunk[i] = 0.f;       // rows never loaded must be finite
-    for (int i = threadIdx.x; i < dm.HR * dm.DU; i += TCA_THREADS) {
-        const int h = i / dm.DU, d = i - h * dm.DU;
-        us[i] = (h < H && d < D) ? u[((int64_t)b * H + h) * D + d] : 0.f;
+    for (int i = threadIdx.x; i < UR * dm.DU; i += TCA_THREADS) {
+        const int r = i / dm.DU, d = i - r * dm.DU;
+        const int h = PACK ? (r & 3) : r;
+        const float x = (h < H && d < D) ? u[((int64_t)b * H + h) * D + d] : 0.f;
+        if (PACK) {
+            uint32_t hi, lo;
+            tca_split(x, hi, lo);
+            us[i] = __uint_as_float(r < 4 ? hi : lo);
+        } else {
+            us[i] = x;
+        }
     }
     for (int i = threadIdx.x; i < dm.HR * dm.LT; i += TCA_THREADS) sc[i] = -INFINITY;
     const int Lb = tca_live_rows(MASKED ? mask + (int64_t)b * L : nullptr, L, lv, &s_lb);   // has the barriers
@@ -256,17 +281,21 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
     for (int c = 0; c < nchunks; ++c) {
         const float* cb = chunk + (c & 1) * CH;
         tca_mbar_wait(&mbar[c & 1], (c >> 1) & 1);
-        tca_score_partials<NT, NT>(cb, us, us, part, dm, warp, lane);
+        tca_score_partials<NT, NT, PACK>(cb, us, us, part, dm, warp, lane);
         __syncthreads();                                 // partials complete; every warp is past the previous chunk
         if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1);
         // ---- online softmax: warp = head (w, w+8), lane = row of the chunk
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int hh = warp + 8 * j;
+            if (PACK && hh >= 4) break;                  // columns 4-7 belong to heads 0-3 (their lo halves)
             const int l = c * TCA_R + lane;
             float s = 0.f;
 #pragma unroll
-            for (int q = 0; q < TCA_KSPLIT; ++q) s += part[(q * TCA_R + lane) * NC + hh];
+            for (int q = 0; q < TCA_KSPLIT; ++q) {
+                s += part[(q * TCA_R + lane) * NC + hh];
+                if (PACK) s += part[(q * TCA_R + lane) * NC + hh + 4];
+            }
             s *= scale;
             const bool live = (hh < H) && (l < Lb) && (!MASKED || lv[l] != 0);
             if (!live) s = -INFINITY;
@@ -278,8 +307,16 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
             m_run[j] = m_new;
             float wgt = e;
             if (DROPOUT && live) wgt = (uniform01(seed, ((uint64_t)b * H + hh) * L + l) >= p_drop) ? e : 0.f;
-            pw[lane * NC + hh] = wgt;
-            if (lane == 0) stat[hh] = corr;
+            if (PACK) {
+                uint32_t hi, lo;
+                tca_split(wgt, hi, lo);
+                pw[lane * NC + hh] = __uint_as_float(hi);
+                pw[lane * NC + hh + 4] = __uint_as_float(lo);
+                if (lane == 0) { stat[hh] = corr; stat[hh + 4] = corr; }
+            } else {
+                pw[lane * NC + hh] = wgt;
+                if (lane == 0) stat[hh] = corr;
+            }
         }
         __syncthreads();                                 // weights and correction factors visible
         // ---- context: rescale, then accumulate this chunk
@@ -290,13 +327,14 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
                 const float c0 = stat[j * 8 + 2 * t], c1 = stat[j * 8 + 2 * t + 1];
                 acc[i][j][0] *= c0; acc[i][j][1] *= c1; acc[i][j][2] *= c0; acc[i][j][3] *= c1;
             }
-        tca_accumulate_t<NT, false>(cb, pw, NC, acc, dm, warp, lane);
+        tca_accumulate_t<NT, false, PACK>(cb, pw, NC, acc, dm, warp, lane);
     }
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int hh = warp + 8 * j;
+            if (PACK && hh >= 4) break;
             stat[NC + hh] = m_run[j];
             stat[2 * NC + hh] = s_run[j];
             if (hh < H) lse[(int64_t)b * H + hh] = m_run[j] + __logf(s_run[j]);
@@ -314,7 +352,9 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_fwd_kernel(
             for (int e = 0; e < 4; ++e) {
                 const int d = mt * 16 + g + ((e & 2) ? 8 : 0);
                 const int hh = j * 8 + 2 * t + (e & 1);
-                if (d < D && hh < H) ctx[((int64_t)b * H + hh) * D + d] = acc[i][j][e] * inv_keep / stat[2 * NC + hh];
+                float v = acc[i][j][e];
+                if (PACK) v += __shfl_xor_sync(0xffffffffu, v, 2);      // column h+4 (the lo half) lives in lane t+2
+                if (d < D && hh < (PACK ? min(H, 4) : H)) ctx[((int64_t)b * H + hh) * D + d] = v * inv_keep / stat[2 * NC + hh];
             }
         }
     }
@@ -350,9 +390,10 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_bwd_kernel(
     extern __shared__ __align__(16) float sm[];
     const int CH = TCA_R * dm.D + TCA_PAD;
     float* chunk = sm;                                   // [2][CH]
-    float* us = chunk + 2 * CH;                          // [HR][DU]
-    float* gs = us + dm.HR * dm.DU;                      // [HR][DU]
-    float* part = gs + dm.HR * dm.DU;                    // [4][R][2*NC]
+    const int UR = PACK4 ? 8 : dm.HR;                    // PACK4: query tables hold [hi | lo] rows (see tca_score_partials)
+    float* us = chunk + 2 * CH;                          // [UR][DU]
+    float* gs = us + UR * dm.DU;                         // [UR][DU]
+    float* part = gs + UR * dm.DU;                       // [4][R][2*NC]
     float* sc = part + TCA_KSPLIT * TCA_R * 2 * NC;      // [HR][LT] scores, then scale*dS
     float* tt = sc + dm.HR * dm.LT;                      // [HR][LT] <dctx,k>, then dropped-out probabilities
     uint64_t* mbar = reinterpret_cast<uint64_t*>(tt + dm.HR * dm.LT);
@@ -374,11 +415,22 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_bwd_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 2 * CH; i += TCA_THREADS) chunk[i] = 0.f;
-    for (int i = threadIdx.x; i < dm.HR * dm.DU; i += TCA_THREADS) {
-        const int h = i / dm.DU, d = i - h * dm.DU;
+    for (int i = threadIdx.x; i < UR * dm.DU; i += TCA_THREADS) {
+        const int r = i / dm.DU, d = i - r * dm.DU;
+        const int h = PACK4 ? (r & 3) : r;
         const bool in = (h < H && d < D);
-        us[i] = in ? u[((int64_t)b * H + h) * D + d] : 0.f;
-        gs[i] = in ? gctx[((int64_t)b * H + h) * D + d] : 0.f;
+        const float xu = in ? u[((int64_t)b * H + h) * D + d] : 0.f;
+        const float xg = in ? gctx[((int64_t)b * H + h) * D + d] : 0.f;
+        if (PACK4) {
+            uint32_t hi, lo;
+            tca_split(xu, hi, lo);
+            us[i] = __uint_as_float(r < 4 ? hi : lo);
+            tca_split(xg, hi, lo);
+            gs[i] = __uint_as_float(r < 4 ? hi : lo);
+        } else {
+            us[i] = xu;
+            gs[i] = xg;
+        }
     }
     for (int i = threadIdx.x; i < dm.HR * dm.LT; i += TCA_THREADS) { sc[i] = -INFINITY; tt[i] = 0.f; }
     const int Lb = tca_live_rows(mask ? mask + (int64_t)b * L : nullptr, L, lv, &s_lb);
@@ -404,13 +456,17 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_bwd_kernel(
         const float* cb = chunk + (n_wait & 1) * CH;
         if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1);      // the other buffer: its readers passed the barrier below
         tca_mbar_wait(&mbar[n_wait & 1], (n_wait >> 1) & 1);
-        tca_score_partials<NT, 2 * NT>(cb, us, gs, part, dm, warp, lane);
+        tca_score_partials<NT, 2 * NT, PACK4>(cb, us, gs, part, dm, warp, lane);
         __syncthreads();
         for (int i = threadIdx.x; i < TCA_R * 2 * NC; i += TCA_THREADS) {
             const int r = i / (2 * NC), col = i - r * (2 * NC);
+            if (PACK4 && (col & 4)) continue;            // columns 4-7 / 12-15 are the lo halves, added below
             float v = 0.f;
 #pragma unroll
-            for (int q = 0; q < TCA_KSPLIT; ++q) v += part[(q * TCA_R + r) * 2 * NC + col];
+            for (int q = 0; q < TCA_KSPLIT; ++q) {
+                v += part[(q * TCA_R + r) * 2 * NC + col];
+                if (PACK4) v += part[(q * TCA_R + r) * 2 * NC + col + 4];
+            }
             const int l = c * TCA_R + r;
             // head tiles are interleaved in the partial table as [u tiles | dctx tiles]
             if (col < NC) {
@@ -466,7 +522,7 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_bwd_kernel(
         const float* cb = chunk + (n_wait & 1) * CH;
         if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1);
         tca_mbar_wait(&mbar[n_wait & 1], (n_wait >> 1) & 1);
-        tca_accumulate_t<NT, true>(cb, sc + c * TCA_R, dm.LT, du, dm, warp, lane);
+        tca_accumulate_t<NT, true, false>(cb, sc + c * TCA_R, dm.LT, du, dm, warp, lane);
         // dbank: C tile = (16-row tile mt2, 8-feature tile nn); tiles dealt round-robin to the warps
         const int ntiles = 2 * dm.KS;
         for (int q = warp; q < ntiles; q += TCA_WARPS) {
@@ -479,7 +535,15 @@ __global__ void __launch_bounds__(TCA_THREADS, 2) attn_q1_tc_bwd_kernel(
                 a[1] = sc[t * dm.LT + l0 + g + 8];
                 a[2] = tt[t * dm.LT + l0 + g];
                 a[3] = tt[t * dm.LT + l0 + g + 8];
-                tca_mma3(cc, a, us[t * dm.DU + nn * 8 + g], gs[t * dm.DU + nn * 8 + g]);
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tca_split(a[k], ah[k], al[k]);
+                const int n = nn * 8 + g;
+                const uint32_t b0h = __float_as_uint(us[t * dm.DU + n]), b0l = __float_as_uint(us[(t + 4) * dm.DU + n]);
+                const uint32_t b1h = __float_as_uint(gs[t * dm.DU + n]), b1l = __float_as_uint(gs[(t + 4) * dm.DU + n]);
+                tca_mma(cc, ah, b0h, b1h);
+                tca_mma(cc, al, b0h, b1h);
+                tca_mma(cc, ah, b0l, b1l);
             } else {
 #pragma unroll
                 for (int j = 0; j < 2 * NT; ++j) {
@@ -538,13 +602,15 @@ static TcaDims tca_dims(int B, int H, int L, int D) {
 }
 static size_t tca_fwd_smem(const TcaDims& dm, int NT) {
     const size_t NC = 8 * NT;
-    const size_t floats = 2 * ((size_t)TCA_R * dm.D + TCA_PAD) + (size_t)dm.HR * dm.DU + (size_t)TCA_KSPLIT * TCA_R * NC + TCA_R * NC +
+    const size_t UR = dm.H <= 4 ? 8 : dm.HR;
+    const size_t floats = 2 * ((size_t)TCA_R * dm.D + TCA_PAD) + UR * dm.DU + (size_t)TCA_KSPLIT * TCA_R * NC + TCA_R * NC +
                           (size_t)dm.HR * dm.LT + 3 * NC;
     return floats * 4 + 16 + ((size_t)dm.L + 15) / 16 * 16;
 }
 static size_t tca_bwd_smem(const TcaDims& dm, int NT) {
     const size_t NC = 8 * NT;
-    const size_t floats = 2 * ((size_t)TCA_R * dm.D + TCA_PAD) + 2 * (size_t)dm.HR * dm.DU + (size_t)TCA_KSPLIT * TCA_R * 2 * NC +
+    const size_t UR = dm.H <= 4 ? 8 : dm.HR;
+    const size_t floats = 2 * ((size_t)TCA_R * dm.D + TCA_PAD) + 2 * UR * dm.DU + (size_t)TCA_KSPLIT * TCA_R * 2 * NC +
                           2 * (size_t)dm.HR * dm.LT;
     return floats * 4 + 16 + ((size_t)dm.L + 15) / 16 * 16;
 }
@@ -574,20 +640,20 @@ extern "C" int mgnns_attn_q1_tc_fwd(const float* u, const float* bank, const flo
     const int NT = (H + 7) / 8;
     const size_t smem = tca_fwd_smem(dm, NT);
     cudaStream_t st = as_stream(stream);
-#define TCA_FWD(NTV, M, DR)                                                                                               \
+#define TCA_FWD(NTV, M, DR, PK)                                                                                           \
     do {                                                                                                                   \
-        cudaFuncSetAttribute(attn_q1_tc_fwd_kernel<NTV, M, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        attn_q1_tc_fwd_kernel<NTV, M, DR><<<B, TCA_THREADS, smem, st>>>(u, bank, mask, dm, scale, p_drop, seed, seed_offset, \
-                                                                        ctx, attn, psum, lse);                            \
+        cudaFuncSetAttribute(attn_q1_tc_fwd_kernel<NTV, M, DR, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        attn_q1_tc_fwd_kernel<NTV, M, DR, PK><<<B, TCA_THREADS, smem, st>>>(u, bank, mask, dm, scale, p_drop, seed,          \
+                                                                            seed_offset, ctx, attn, psum, lse);            \
     } while (0)
-#define TCA_FWD_FLAGS(NTV)                                           \
+#define TCA_FWD_FLAGS(NTV, PK)                                       \
     do {                                                             \
-        if (mask != nullptr && p_drop > 0.f) TCA_FWD(NTV, true, true);       \
-        else if (mask != nullptr) TCA_FWD(NTV, true, false);         \
-        else if (p_drop > 0.f) TCA_FWD(NTV, false, true);            \
-        else TCA_FWD(NTV, false, false);                             \
+        if (mask != nullptr && p_drop > 0.f) TCA_FWD(NTV, true, true, PK);   \
+        else if (mask != nullptr) TCA_FWD(NTV, true, false, PK);     \
+        else if (p_drop > 0.f) TCA_FWD(NTV, false, true, PK);        \
+        else TCA_FWD(NTV, false, false, PK);                         \
     } while (0)
-    if (NT == 1) TCA_FWD_FLAGS(1); else TCA_FWD_FLAGS(2);
+    if (H <= 4) TCA_FWD_FLAGS(1, true); else if (NT == 1) TCA_FWD_FLAGS(1, false); else TCA_FWD_FLAGS(2, false);
 #undef TCA_FWD_FLAGS
 #undef TCA_FWD
     MG_LAUNCH_CHECK("attn_q1_tc_fwd");
