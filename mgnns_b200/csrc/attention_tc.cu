@@ -123,12 +123,15 @@ __device__ __forceinline__ void tca_score_partials(const float* __restrict__ cb,
     const int mt = warp & 1, ks = warp >> 1;
     const int ks4 = (dm.KS + TCA_KSPLIT - 1) / TCA_KSPLIT;
     const int kk0 = ks * ks4, kk1 = min(dm.KS, kk0 + ks4);
-    float c[NTT][4];
+    // two accumulator sets for alternate K steps: halves the dependent-MMA chain (the kernel is latency bound)
+    float c2[2][NTT][4];
 #pragma unroll
-    for (int j = 0; j < NTT; ++j) { c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f; }
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < NTT; ++j) { c2[q][j][0] = c2[q][j][1] = c2[q][j][2] = c2[q][j][3] = 0.f; }
     const float* ar0 = cb + (mt * 16 + g) * dm.D;
     const float* ar1 = ar0 + 8 * dm.D;
-    for (int kk = kk0; kk < kk1; ++kk) {
+    auto step = [&](int kk, float (&c)[NTT][4]) {
         const int k0 = kk * 8 + t;
         float a[4];
         a[0] = ar0[k0];
@@ -153,7 +156,18 @@ __device__ __forceinline__ void tca_score_partials(const float* __restrict__ cb,
                 tca_mma3_pre(c[j], ah, al, on ? qp[0] : 0.f, on ? qp[4] : 0.f);
             }
         }
+    };
+    int kk = kk0;
+    for (; kk + 2 <= kk1; kk += 2) {
+        step(kk, c2[0]);
+        step(kk + 1, c2[1]);
     }
+    if (kk < kk1) step(kk, c2[0]);
+    float c[NTT][4];
+#pragma unroll
+    for (int j = 0; j < NTT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[j][e] = c2[0][j][e] + c2[1][j][e];
     constexpr int NC = 8 * NTT;
     float* pp = part + (ks * TCA_R + mt * 16 + g) * NC + 2 * t;
 #pragma unroll

@@ -487,13 +487,15 @@ def _spmm_raw(rowptr, col, val, x, n_rows):
     if rowptr.numel() != n_rows + 1:
         raise RuntimeError("mgnns::spmm_csr: rowptr has %d entries, expected %d" % (rowptr.numel(), n_rows + 1))
     if (batch >= _HUB_MIN_BATCH and col.numel() >= _HUB_MIN_NNZ and F % 4 == 0 and F <= 512
-            and x.data_ptr() % 16 == 0 and os.environ.get("MGNNS_SPMM_HUB", "1") != "0"):
-        # batched features on a big graph: persistent kernel with the hub neighbour rows staged in shared memory
-        # Rows of 300 floats start at 16-byte but not 128-byte aligned addresses, and a misaligned 128-bit warp load
-        # costs up to twice the L1 data-pipe wavefronts of an aligned one — the pipe this kernel saturates (ncu: 82 %).
-        # One streaming copy into rows padded to a multiple of 32 floats (128 B) buys that back.
+            and x.data_ptr() % 16 == 0 and os.environ.get("MGNNS_SPMM_HUB", "0") == "1"):
+        # Opt-in: persistent kernel with the hub neighbour rows staged in shared memory.  Measured on cfg 2 (B200):
+        # 11.97 ms against 11.33 ms for the plain kernel — the gather is bound by the L1 global-load return path
+        # (64 B/clk/SM: 17.6 of 18.2 TB/s), which the plain kernel already saturates; moving the 31 % hub edges to
+        # shared memory (128 B/clk) is offset by this kernel's lower occupancy.
+        # MGNNS_SPMM_PAD=1 copies X into rows padded to 128 bytes first (rows of 300 floats start at 16-byte aligned
+        # addresses): measured, it buys nothing — 13.4 ms with the copy — so alignment is not what limits the gather.
         ldx = F
-        if os.environ.get("MGNNS_SPMM_PAD", "1") != "0" and F % 32 != 0:
+        if os.environ.get("MGNNS_SPMM_PAD", "0") == "1" and F % 32 != 0:
             ldx = (F + 31) // 32 * 32
             with _timed("spmm_pad"):
                 xp = torch.empty((batch, n_cols, ldx), device=x.device, dtype=torch.float32)

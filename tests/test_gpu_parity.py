@@ -140,7 +140,7 @@ def test_spmm_matches_dense(dev, n, F, batch):
 def test_spmm_hub_staged_kernel_matches_dense_and_plain_kernel(ops, dev, n, F, batch, density):
     """The persistent SpMM with shared-memory hub rows (batched features, nnz >= 100k): hub columns, a 1,500-edge hub
     ROW (segments combined with vector atomics), an empty row; forward and the transpose product of the backward,
-    against float64 and against the plain kernel (MGNNS_SPMM_HUB=0)."""
+    against float64 and against the plain kernel (the default; the hub kernel is MGNNS_SPMM_HUB=1)."""
     from mgnns_b200.api.graph_util import CSRAdjacency
     adj = random_adj(n, n, density, seed=n)
     g = torch.Generator().manual_seed(n + 7)
@@ -155,21 +155,26 @@ def test_spmm_hub_staged_kernel_matches_dense_and_plain_kernel(ops, dev, n, F, b
     x = rnd(batch, n, F, seed=F)
     xg = x.to(dev).requires_grad_()
     ops.KernelTimers.reset(['spmm_hub', 'spmm_csr'])
-    y = csr.spmm(xg)
-    r = rnd(*y.shape, seed=1)
-    (y * r.to(dev)).sum().backward()
-    torch.cuda.synchronize()
-    assert ops.KernelTimers.mean_ms('spmm_hub')[1] == 2 and ops.KernelTimers.mean_ms('spmm_csr')[1] == 0
+    os.environ['MGNNS_SPMM_HUB'] = '1'
+    try:
+        y = csr.spmm(xg)
+        r = rnd(*y.shape, seed=1)
+        (y * r.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            os.environ['MGNNS_SPMM_PAD'] = '1'
+            y_pad = csr.spmm(x.to(dev))                  # rows copied to a 128-byte stride first
+            del os.environ['MGNNS_SPMM_PAD']
+    finally:
+        del os.environ['MGNNS_SPMM_HUB']
+    assert ops.KernelTimers.mean_ms('spmm_hub')[1] == 3 and ops.KernelTimers.mean_ms('spmm_csr')[1] == 0
     ops.KernelTimers.reset([])
+    assert (y_pad - y).abs().max().item() < 1e-6
     close(y, torch.matmul(adj.double(), x.double()), 1e-5, 1e-5)
     close(xg.grad, torch.matmul(adj.double().t(), r.double()), 1e-5, 1e-5)
     assert (y[:, 3] == 0).all()
-    os.environ['MGNNS_SPMM_HUB'] = '0'
-    try:
-        with torch.no_grad():
-            y0 = csr.spmm(x.to(dev))
-    finally:
-        del os.environ['MGNNS_SPMM_HUB']
+    with torch.no_grad():
+        y0 = csr.spmm(x.to(dev))                         # the default (plain) kernel
     assert (y - y0).abs().max().item() < 1e-5
 
 
@@ -1057,6 +1062,50 @@ def test_cfg5_shaped_model_16_heads_large_label_graphs_vs_oracle(dev):
                   'img_object_text_multi_head_att.1.slf_attn.fc.weight', 'lstm.weight_hh_l1_reverse', 'liner_img_place.weight',
                   'multi_linear_1.weight'):
             np.testing.assert_allclose(params[n].grad.norm().item(), P[n].grad.norm().item(), rtol=5e-3, err_msg=n)
+
+
+def test_cfg5_full_size_32_sample_slice_vs_oracle(dev, ops):
+    """BASELINE.json configs[4] at its full model size — V = 50,000 vocabulary, 4096 object + 4096 scene label nodes
+    (A_hat 0.4 % full: the label GCN runs on the SpMM + tcgen05 path with 4096 rows), 16 attention heads (two head
+    tiles in the tensor-core attention) — on a 32-sample slice of the batch against the CPU oracle: logits within
+    1e-3 rel / 1e-4 abs, identical arg-max, gradient norms of one parameter per kernel family."""
+    from mgnns_b200.api.multi_gcn import IdentityTrunk, Multi_GCN_Multihead_Att
+    from mgnns_b200.api.text_gcn import Model as TextModel
+    n_obj = n_plc = 4096
+    cfg = dict(H.MODEL_CFG, B=32, V=50000, seed=51, n_head=16, n_obj=n_obj, n_plc=n_plc, object_t=0.04, place_t=0.04)
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=51, docs=3000)
+    adj_o, adj_p = synth.synthetic_label_graph(n_obj, seed=80), synth.synthetic_label_graph(n_plc, seed=365)
+    opt = dict(emb_path='', bidirectional=True, hidden_size=150, emb_size=300, num_layers=2, dropout=0.5,
+               emb_type='random', vocab_size=cfg['V'], stack_num=2, n_head=16, d_kv=128, is_regu=False)
+    vocab = ['PAD', 'UNK'] + ['w%d' % i for i in range(2, cfg['V'])]
+    tm = TextModel(7, 300, vocab, cfg['ngram'], 0.5, count, emap, pmi=torch.zeros(count, 1))
+    model = Multi_GCN_Multihead_Att(opt, 7, tm, IdentityTrunk(), IdentityTrunk(), n_obj, n_plc, object_t=0.04, place_t=0.04,
+                                    in_channel=300, object_adj_file=adj_o, place_adj_file=adj_p)
+    synth.fill_parameters(model, seed=51)
+    model = model.to(dev).eval()
+    assert ops.attn_uses_tensor_cores(16, 196, 300) and ops.attn_uses_tensor_cores(16, 100, 300)
+    text, lens, mask = synth.make_texts(cfg['B'], cfg['V'], cfg['L'], seed=51)
+    fo, fp = synth.make_fmaps(cfg['B'], seed=51), synth.make_fmaps(cfg['B'], seed=52)
+    oinp, pinp = synth.label_inputs(cfg['B'], n_obj, n_plc, seed=3)
+    labels = synth.make_labels(cfg['B'], 7, seed=51)
+    model.branch_streams = True
+    logits = model(text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    torch.nn.functional.cross_entropy(logits, labels.to(dev)).backward()
+    csr = model._adj_csr('object_A')
+    assert 0.003 < csr.nnz / n_obj ** 2 < 0.006
+    P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    watch = ('gc1.weight', 'gc2.weight', 'object_attention.w_k.weight', 'text_img_place_multi_head_att.0.slf_attn.w_qs.weight',
+             'img_object_text_multi_head_att.1.slf_attn.w_vs.weight', 'lstm.weight_hh_l0', 'liner_img_object.weight')
+    for k in watch:
+        P[k].requires_grad_()
+    query = torch.from_numpy(synth.label_graphs()['label_glove'])
+    ref = O.model_forward(P, text, lens, mask, fo, fp, oinp[0], pinp[0], query, lambda u, v: emap[u, v], cfg)
+    close(logits, ref, 1e-3, 1e-4)
+    assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
+    torch.nn.functional.cross_entropy(ref, labels).backward()
+    params = dict(model.named_parameters())
+    for n in watch:
+        np.testing.assert_allclose(params[n].grad.norm().item(), P[n].grad.norm().item(), rtol=5e-3, err_msg=n)
 
 
 def test_graphed_train_step_matches_eager_steps(dev, ops):
