@@ -36,7 +36,7 @@ WORKLOADS = {
                       "ResNet trunks excluded (inputs are trunk outputs)"),
     'cfg5': dict(V=50000, n_obj=4096, n_plc=4096, n_head=16, docs=200000, object_t=0.04, place_t=0.04,
                  name="cfg5 stress training step: %d samples/GPU, V=50000 word graph (PMI counted on the GPU), 4096 object "
-                      "+ 4096 scene label nodes (A_hat 0.4% full), 16 attention heads; fwd+CE+bwd+clip+Adam; trunks excluded"),
+                      "+ 4096 scene label nodes (A_hat 0.4%% full), 16 attention heads; fwd+CE+bwd+clip+Adam; trunks excluded"),
 }
 WORKLOAD = WORKLOADS['cfg4']['name']
 

@@ -167,6 +167,7 @@ def test_spmm_hub_staged_kernel_matches_dense_and_plain_kernel(ops, dev, n, F, b
             del os.environ['MGNNS_SPMM_PAD']
     finally:
         del os.environ['MGNNS_SPMM_HUB']
+    torch.cuda.synchronize()
     assert ops.KernelTimers.mean_ms('spmm_hub')[1] == 3 and ops.KernelTimers.mean_ms('spmm_csr')[1] == 0
     ops.KernelTimers.reset([])
     assert (y_pad - y).abs().max().item() < 1e-6
