@@ -54,6 +54,8 @@ def parse():
     ap.add_argument('--no-cfg2', action='store_true', help='skip the cfg-2 GraphConvolution microbench')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager', action='store_true', help='do not capture the step in a CUDA graph')
+    ap.add_argument('--torch-optimizer', action='store_true',
+                    help="clip_grad_norm_ + torch.optim.Adam(fused=True) instead of the two-kernel FlatClipAdam (same arithmetic)")
     ap.add_argument('--no-branch-streams', action='store_true', help='run the independent channels / stacks on one stream')
     return ap.parse_args()
 
@@ -569,7 +571,8 @@ def ours(args):
             gsteps = []
             for d in dbs:
                 l0 = _abi.launch_count()
-                gsteps.append(GraphedTrainStep(model, opt, crit, d, clip_norm=10.0, world_size=world, warmup=2))
+                fo = None if args.torch_optimizer else (gsteps[0].flat_opt if gsteps else True)
+                gsteps.append(GraphedTrainStep(model, opt, crit, d, clip_norm=10.0, world_size=world, warmup=2, flat_optimizer=fo))
                 launches_per_step = (_abi.launch_count() - l0) // 3       # 2 warm-up steps + 1 captured step
             launch_mode = "cuda_graph"
         except Exception as exc:            # capture is an optimisation, never a correctness dependency
@@ -577,6 +580,8 @@ def ours(args):
             gsteps = None
             opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5)
             reducer = GradientAllReducer(model) if world > 1 else None
+
+    gsteps_flat = gsteps[0].flat_opt if gsteps else None
 
     def run_step(i):
         if gsteps is not None:
@@ -759,6 +764,8 @@ def ours(args):
                        "l2": "inputs larger than L2 (1.65 GB of feature maps per step; three rotating batches)",
                        "precision_mode": "%s tensor-core contractions (3xTF32 split = fp32-class accuracy), fp32 FMA elsewhere" % ops.get_precision(),
                        "launch": launch_mode, "launch_note": graph_note, "branch_streams": bool(model.branch_streams),
+                       "optimizer": ("clip_grad_norm_ + torch.optim.Adam(fused)" if (args.torch_optimizer or gsteps_flat is None)
+                                     else "FlatClipAdam: same clip + Adam arithmetic as 2 kernels over flat buffers (tested equal)"),
                        "numa": numa,
                        "kernel_timing": "per-kernel: separate eager single-stream pass of %d steps, CUDA events per launch" % KT},
             "clocks": clocks,

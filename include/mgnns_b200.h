@@ -345,6 +345,19 @@ int mgnns_confusion_count(const float* scores, int64_t ld, const int64_t* target
 int mgnns_label_cooccurrence(const int32_t* labels, const int32_t* lens, int64_t n_images, int max_len,
                              int C, int64_t* nums, int64_t* adj, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * clip_grad_norm_ + Adam over flat buffers (two launches; mgnns_b200.optim.FlatClipAdam is the host side).
+ *   mgnns_sqnorm_f32:    *out = sum of squares of g[0..n) (double; zeroed here)
+ *   mgnns_clip_adam_f32: g *= min(1, max_norm/(sqrt(*sqnorm) + 1e-6)) in place; for every segment s (gradient range
+ *     [seg_g[s], seg_g[s+1]), all multiples of 4) with seg_p[s] >= 0, torch.optim.Adam's update (L2 weight decay,
+ *     bias correction from the device step counter *step, which the caller increments first) on p/m/v at seg_p[s].
+ * ref: engine/Multi_GCN_Multihead_Att_engine.py:850-851, Tumblr_Multi_GCN_Multihead_Att.py:164
+ * ------------------------------------------------------------------------- */
+int mgnns_sqnorm_f32(const float* g, int64_t n, double* out, void* stream);
+int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t* seg_p, const float* seg_lr,
+                        const float* seg_wd, int n_seg, float* p, float* m, float* v, const double* sqnorm,
+                        float max_norm, float beta1, float beta2, float eps, const int64_t* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

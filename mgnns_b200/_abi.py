@@ -60,6 +60,8 @@ SIGNATURES = {
     "mgnns_pmi_scatter_targets": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "mgnns_pmi_row_reduce": (c_int, [P, P, c_int, c_int, P, P, P, P]),
     "mgnns_pmi_compact": (c_int, [P, P, P, P, c_int, P, P, P]),
+    "mgnns_sqnorm_f32": (c_int, [P, c_int64, P, P]),
+    "mgnns_clip_adam_f32": (c_int, [P, c_int64, P, P, P, P, c_int, P, P, P, P, c_float, c_float, c_float, c_float, P, P]),
     "mgnns_confusion_count": (c_int, [P, c_int64, P, c_int, c_int, P, P, P]),
     "mgnns_label_cooccurrence": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),

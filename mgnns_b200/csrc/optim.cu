@@ -1,0 +1,128 @@
+// clip_grad_norm_ + Adam over flat buffers, two launches per step
+// (ref: engine/Multi_GCN_Multihead_Att_engine.py:850-851 — nn.utils.clip_grad_norm_(model.parameters(), 10.0) then
+//  optimizer.step() with torch.optim.Adam(model.get_config_optim(lr, lrp), lr, weight_decay), entry:164).
+//
+// torch runs this as ~10 multi-tensor launches over ~150 separate tensors (0.5 ms of the 9.3 ms step, measured alone on
+// the GPU at ~30 % of HBM bandwidth).  Here the gradients of ALL parameters live in one flat buffer (the one the
+// gradient all-reduce uses) and the optimizer-owned parameters and their Adam moments in three more, so the step is
+//   1. sqnorm:     sum of squares of the whole gradient buffer (double accumulation)
+//   2. clip_adam:  g *= min(1, max_norm / (norm + 1e-6)) written back (never-stepped parameters keep accumulating
+//                  their scaled gradients, as with the reference's optimizer.zero_grad()), and for the elements a
+//                  segment table maps to an optimizer-owned parameter, torch's Adam update with that group's lr and
+//                  weight decay:  g += wd*p; m += (1-b1)(g-m); v = b2 v + (1-b2) g^2;
+//                  p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// both streaming at HBM speed with 128-bit accesses.
+#include "common.cuh"
+
+namespace mgnns {
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+    double acc = 0.0;
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const float v = g[(n4 << 2) + threadIdx.x];
+        acc += (double)v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        atomicAdd(out, t);
+    }
+}
+
+constexpr int OPT_MAX_SEG = 1024;
+
+// segments: gradient-buffer ranges [seg_g[s], seg_g[s+1]) in ascending order; seg_p[s] = offset of the same tensor in
+// the parameter / moment buffers or -1 when the optimizer does not own it
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ g, int64_t n, const int64_t* __restrict__ seg_g,
+                                                        const int64_t* __restrict__ seg_p, const float* __restrict__ seg_lr,
+                                                        const float* __restrict__ seg_wd, int n_seg,
+                                                        float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                        const double* __restrict__ sqnorm, float max_norm, float beta1,
+                                                        float beta2, float eps, const int64_t* __restrict__ step) {
+    __shared__ int64_t s_g[OPT_MAX_SEG + 1];
+    for (int i = threadIdx.x; i <= n_seg; i += blockDim.x) s_g[i] = seg_g[i];
+    __syncthreads();
+    const float norm = (float)sqrt(*sqnorm);
+    const float coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    const double t = (double)(*step);
+    const float bc1 = (float)(1.0 - pow((double)beta1, t));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    // every tensor starts at a multiple of 4 floats in both buffers (the host pads), so a float4 never straddles a segment
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i << 2;
+        int lo = 0, hi = n_seg;                      // last segment with s_g[seg] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_g[mid] <= e) lo = mid; else hi = mid;
+        }
+        float4 gv = *reinterpret_cast<float4*>(g + e);
+        gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
+        *reinterpret_cast<float4*>(g + e) = gv;
+        const int64_t po = seg_p[lo];
+        if (po < 0) continue;
+        const int64_t pe = po + (e - s_g[lo]);
+        const float lr = seg_lr[lo], wd = seg_wd[lo];
+        float4 pv = *reinterpret_cast<float4*>(p + pe);
+        float4 mv = *reinterpret_cast<float4*>(m + pe);
+        float4 vv = *reinterpret_cast<float4*>(v + pe);
+        const float step_size = lr / bc1;
+#define MG_ADAM(c)                                                         \
+        {                                                                  \
+            const float gg = gv.c + wd * pv.c;                             \
+            mv.c = mv.c + (1.f - beta1) * (gg - mv.c);                     \
+            vv.c = beta2 * vv.c + (1.f - beta2) * gg * gg;                 \
+            pv.c -= step_size * mv.c / (sqrtf(vv.c) / bc2_sqrt + eps);     \
+        }
+        MG_ADAM(x) MG_ADAM(y) MG_ADAM(z) MG_ADAM(w)
+#undef MG_ADAM
+        *reinterpret_cast<float4*>(p + pe) = pv;
+        *reinterpret_cast<float4*>(m + pe) = mv;
+        *reinterpret_cast<float4*>(v + pe) = vv;
+    }
+}
+
+}  // namespace mgnns
+
+using namespace mgnns;
+
+extern "C" int mgnns_sqnorm_f32(const float* g, int64_t n, double* out, void* stream) {
+    MG_REQUIRE(n >= 0 && out, "sqnorm: bad argument");
+    cudaStream_t st = as_stream(stream);
+    MG_REQUIRE(cudaMemsetAsync(out, 0, sizeof(double), st) == cudaSuccess, "sqnorm: memset failed");
+    if (n == 0) return 0;
+    MG_REQUIRE(g && aligned16(g), "sqnorm: the buffer must be 16-byte aligned");
+    int blocks = (int)((n / 4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    sqnorm_kernel<<<blocks, 256, 0, st>>>(g, n, out);
+    MG_LAUNCH_CHECK("sqnorm");
+    return 0;
+}
+
+extern "C" int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t* seg_p, const float* seg_lr,
+                                   const float* seg_wd, int n_seg, float* p, float* m, float* v, const double* sqnorm,
+                                   float max_norm, float beta1, float beta2, float eps, const int64_t* step, void* stream) {
+    MG_REQUIRE(n >= 0 && n_seg >= 1 && n_seg <= OPT_MAX_SEG, "clip_adam: between 1 and %d segments", OPT_MAX_SEG);
+    if (n == 0) return 0;
+    MG_REQUIRE(g && seg_g && seg_p && seg_lr && seg_wd && p && m && v && sqnorm && step, "clip_adam: null pointer");
+    MG_REQUIRE((n & 3) == 0 && aligned16(g) && aligned16(p) && aligned16(m) && aligned16(v),
+               "clip_adam: buffers must be 16-byte aligned and padded to a multiple of 4 floats");
+    int blocks = (int)((n / 4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    clip_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, seg_g, seg_p, seg_lr, seg_wd, n_seg, p, m, v, sqnorm, max_norm,
+                                                           beta1, beta2, eps, step);
+    MG_LAUNCH_CHECK("clip_adam");
+    return 0;
+}

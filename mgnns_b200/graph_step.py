@@ -16,7 +16,11 @@ from . import ops
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, criterion, batch, clip_norm=10.0, world_size=1, plan_capacity=None,
-                 warmup=3):
+                 warmup=3, flat_optimizer=None):
+        """`flat_optimizer`: None = clip_grad_norm_ + optimizer.step() as the reference calls them (engine:850-851);
+        True = the same arithmetic as two kernels over flat buffers (mgnns_b200.optim.FlatClipAdam, built from
+        `optimizer`, which must be torch.optim.Adam); or an existing FlatClipAdam shared between several
+        GraphedTrainStep objects of the same model (one per static batch)."""
         """batch: dict of STATIC tensors — text i64 [B,L], mask f32 [B,L], fo/fp f32 [B,2048,14,14],
         oinp/pinp, labels (all on the model's device) and lens (int64, CPU)."""
         self.model, self.opt, self.crit, self.batch = model, optimizer, criterion, batch
@@ -36,6 +40,8 @@ class GraphedTrainStep:
         self.graph_update = None
         self._flat = None
         self._views = None
+        self._fg = None
+        self.flat_opt = flat_optimizer
         self._warmup = warmup
         self.recaptures = 0
         self.time_allreduce = False
@@ -79,17 +85,12 @@ class GraphedTrainStep:
     def _pack_grads(self):
         """Gather every gradient into one flat buffer with a multi-tensor copy; afterwards each p.grad aliases
         its slice (no copy back), which is what the all-reduce, clip_grad_norm_ and the optimizer then use."""
-        params = [p for p in self.model.parameters() if p.grad is not None]
-        if self._flat is None:
-            total = sum(p.numel() for p in params)
-            self._flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
-            self._views, off = [], 0
-            for p in params:
-                self._views.append(self._flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-        torch._foreach_copy_(self._views, [p.grad for p in params])
-        for p, v in zip(params, self._views):
-            p.grad = v
+        from .optim import FlatGradients
+        if self._fg is None:
+            fo = self.flat_opt if (self.flat_opt is not None and self.flat_opt is not True) else None
+            self._fg = fo.grads if fo is not None else FlatGradients(self.model.parameters())
+            self._flat, self._views = self._fg.flat, self._fg.views
+        self._fg.pack()
 
     def _allreduce(self):
         """The one collective of the step: flat NCCL all-reduce of the gradients (SUM; the / world follows)."""
@@ -109,13 +110,20 @@ class GraphedTrainStep:
         return loss.detach()
 
     def _clip_and_step(self):
-        torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
-        self.opt.step()
+        if self.flat_opt is None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.clip_norm)
+            self.opt.step()
+            return
+        if self.flat_opt is True:
+            from .optim import FlatClipAdam
+            self.flat_opt = FlatClipAdam(self.opt, self._fg, self.clip_norm)
+        self.flat_opt.step()
 
     def _step(self):
         loss = self._forward_backward()
-        if self.world > 1:
+        if self.world > 1 or self.flat_opt is not None:
             self._pack_grads()
+        if self.world > 1:
             self._allreduce()
             self._flat.div_(self.world)
         self._clip_and_step()
@@ -133,9 +141,10 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             self.lens_key.copy_(lens_cpu)                  # in-place: bumps the version, so the plan cache misses on purpose
             self.plan = self.model.make_text_plan(self.lens_key, L, capacity=cap)
-            self._flat, self._views = None, None
-            for p in self.model.parameters():
-                p.grad = None
+            if self.flat_opt is None:
+                self._flat, self._views, self._fg = None, None, None
+                for p in self.model.parameters():
+                    p.grad = None
             self.recaptures += 1
             self._capture(max(1, self._warmup - 1))
             return

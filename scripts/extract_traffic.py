@@ -15,7 +15,9 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
-        'lts__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active']
+        'lts__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct',
+        'l1tex__m_xbar2l1tex_read_bytes.sum']
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}
 
 
@@ -51,12 +53,12 @@ def main():
                                   'dram_read': d.get('dram__bytes_read.sum'), 'dram_write': d.get('dram__bytes_write.sum'),
                                   'us_under_ncu': d.get('gpu__time_duration.sum'), 'report': os.path.basename(rep)}
     print("| timer | kernel | grid x block | time (us) | DRAM read (MB) | DRAM write (MB) | DRAM % | tensor pipe % | "
-          "issue active % | warps active % | regs | L2 hit % |\n|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+          "issue active % | warps active % | regs | L2 hit % | L1 data pipe % | L1 hit % | L2->L1 (GB) |\n|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for alias, name, grid, block, d in table:
         g = lambda k, s=1.0: ('%.1f' % (d[k] / s)) if k in d else '-'
-        print("| %s | `%s` | %s x %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
+        print("| %s | `%s` | %s x %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
             alias, name, grid, block, g(WANT[0]), g(WANT[1], 1e6), g(WANT[2], 1e6), g(WANT[3]), g(WANT[4]), g(WANT[8]),
-            g(WANT[5]), g(WANT[6]), g(WANT[7])))
+            g(WANT[5]), g(WANT[6]), g(WANT[7]), g(WANT[9]), g(WANT[10]), g(WANT[11], 1e9)))
     if traffic:
         path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         old = json.load(open(path)) if os.path.exists(path) else {}

@@ -23,28 +23,24 @@ model = bench.build_model(dev, emap, count).train()
 model.branch_streams = os.environ.get('MGNNS_BRANCH_STREAMS', '1') == '1'
 opt = torch.optim.Adam(model.get_config_optim(5e-5, 0.1), lr=5e-5, weight_decay=1e-5, capturable=True, fused=True)
 d = bench.to_device(bench.host_batch(B, 0), dev, B)
-g = GraphedTrainStep(model, opt, torch.nn.CrossEntropyLoss(), d, clip_norm=10.0, world_size=1, warmup=2)
+g = GraphedTrainStep(model, opt, torch.nn.CrossEntropyLoss(), d, clip_norm=10.0, world_size=1, warmup=2,
+                     flat_optimizer=None if os.environ.get('MGNNS_TORCH_OPT') == '1' else True)
 for _ in range(3):
     g.replay()
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(3):
-        g.replay()
+    g.replay()                       # exactly one step in the trace
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), 'trace.json')
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))['traceEvents'] if e.get('cat') in ('kernel', 'gpu_memcpy', 'gpu_memset') and 'dur' in e]
 ev.sort(key=lambda e: e['ts'])
-# last replay only: split on the largest gaps
-t_end = max(e['ts'] + e['dur'] for e in ev)
-gaps = sorted(((ev[i + 1]['ts'] - max(x['ts'] + x['dur'] for x in ev[:i + 1][-50:]), i) for i in range(len(ev) - 1)), reverse=True)[:2]
-cut = max(i for _, i in gaps) + 1
-step = ev[cut:]
+step = ev
 t0 = step[0]['ts']
 span = max(e['ts'] + e['dur'] for e in step) - t0
-print("last replay: %d GPU activities over %.3f ms on %d streams" % (len(step), span / 1e3, len({e['args'].get('stream') for e in step})))
+print("one replay: %d GPU activities over %.3f ms on %d streams" % (len(step), span / 1e3, len({e['args'].get('stream') for e in step})))
 # sweep line: concurrency histogram and per-kernel "alone" time
 pts = []
 for i, e in enumerate(step):

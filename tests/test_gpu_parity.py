@@ -1109,10 +1109,63 @@ def test_cfg5_full_size_32_sample_slice_vs_oracle(dev, ops):
         np.testing.assert_allclose(params[n].grad.norm().item(), P[n].grad.norm().item(), rtol=5e-3, err_msg=n)
 
 
-def test_graphed_train_step_matches_eager_steps(dev, ops):
+def test_flat_clip_adam_matches_clip_grad_norm_plus_torch_adam(dev):
+    """mgnns_sqnorm_f32 + mgnns_clip_adam_f32 (two launches over flat buffers) against the reference's sequence —
+    optimizer.zero_grad(); backward; clip_grad_norm_(model.parameters(), 10); torch.optim.Adam.step() with the twelve
+    parameter groups of get_config_optim — over four steps with a clip that bites (max_norm 0.05) and one that does
+    not: same parameters, same Adam moments, same (scaled, accumulating) gradients of the never-stepped parameters."""
+    from mgnns_b200.optim import FlatClipAdam, FlatGradients
+    cfg = dict(H.MODEL_CFG, B=8, seed=17)
+    zp_seed = 17
+    emap, count = synth.synthetic_edge_map(cfg['V'], seed=zp_seed, docs=400)
+    text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
+    args = (text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
+    for max_norm in (0.05, 1e6):
+        ma = build_model(dev, cfg, emap, count).eval()         # eval: no dropout, so both runs see the same gradients
+        mb = build_model(dev, cfg, emap, count).eval()
+        oa = torch.optim.Adam(ma.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=1e-2)
+        ob = torch.optim.Adam(mb.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=1e-2)
+        fg = flat = None
+        for step in range(4):
+            oa.zero_grad()
+            torch.nn.functional.cross_entropy(ma(*args), labels.to(dev)).backward()
+            na = torch.nn.utils.clip_grad_norm_(ma.parameters(), max_norm=max_norm)
+            oa.step()
+            if flat is None:
+                ob.zero_grad()
+            else:
+                flat.zero_grad()
+            torch.nn.functional.cross_entropy(mb(*args), labels.to(dev)).backward()
+            if fg is None:
+                fg = FlatGradients(mb.parameters())
+            fg.pack()
+            if flat is None:
+                flat = FlatClipAdam(ob, fg, max_norm)
+            flat.step()
+            np.testing.assert_allclose(flat.total_norm(), float(na), rtol=2e-5)
+        pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+        moved = 0
+        for n in pa:
+            close(pb[n], pa[n], 2e-5, 1e-7, msg=n)
+            if pa[n].grad is not None:
+                close(pb[n].grad, pa[n].grad, 2e-4, 1e-9, msg='grad ' + n)
+        for p in flat.owned_params:
+            st = oa.state[[q for n, q in pa.items() if pb[n] is p][0]]
+            o = flat.p_flat.data_ptr()
+            off = (p.data_ptr() - o) // 4
+            close(flat.m_flat[off:off + p.numel()].view_as(p), st['exp_avg'], 2e-5, 1e-9)
+            close(flat.v_flat[off:off + p.numel()].view_as(p), st['exp_avg_sq'], 2e-5, 1e-12)
+            moved += 1
+        assert moved > 80 and int(flat.step_count) == 4
+        assert pb['multi_linear_1.weight'].grad is not None and pb['multi_linear_1.weight'] not in set(flat.owned_params)
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_graphed_train_step_matches_eager_steps(dev, ops, flat):
     """GraphedTrainStep (whole step captured as one CUDA graph: four-stream forward/backward, deferred weight
-    gradients, clip, fused Adam) against the same three steps run eagerly on one stream — eval mode, so no dropout
-    randomness; parameters must agree to summation-order noise.  Also exercises update_lengths() on a second batch."""
+    gradients, clip, Adam — torch's fused Adam or, flat=True, the two-kernel FlatClipAdam) against the same three
+    steps run eagerly on one stream with clip_grad_norm_ + torch.optim.Adam — eval mode, so no dropout randomness;
+    parameters must agree to summation-order noise.  Also exercises update_lengths() on a second batch."""
     from mgnns_b200.graph_step import GraphedTrainStep
     cfg = dict(H.MODEL_CFG, B=16, V=300, seed=51)
     emap, count = synth.synthetic_edge_map(cfg['V'], seed=51, docs=500)
@@ -1149,7 +1202,8 @@ def test_graphed_train_step_matches_eager_steps(dev, ops):
     m_g.branch_streams = True
     static = {k: (v.clone() if torch.is_tensor(v) and k != 'lens' else v) for k, v in batches[0].items()}
     p0 = {n: p.detach().clone() for n, p in m_g.named_parameters()}
-    g = GraphedTrainStep(m_g, o_g, crit, static, clip_norm=10.0, world_size=1, warmup=1, plan_capacity=16 * 100)
+    g = GraphedTrainStep(m_g, o_g, crit, static, clip_norm=10.0, world_size=1, warmup=1, plan_capacity=16 * 100,
+                         flat_optimizer=True if flat else None)
     with torch.no_grad():
         for n, p in m_g.named_parameters():
             p.copy_(p0[n])
@@ -1157,6 +1211,11 @@ def test_graphed_train_step_matches_eager_steps(dev, ops):
         for k, v in st.items():
             if torch.is_tensor(v):
                 v.zero_()
+    if flat:
+        assert len(o_g.state) == 0 and g.flat_opt.p_flat.numel() > 1e6
+        g.flat_opt.m_flat.zero_()
+        g.flat_opt.v_flat.zero_()
+        g.flat_opt.step_count.zero_()
     # Like the reference engine (optimizer.zero_grad(), engine:841), the step only clears the gradients of the
     # parameters the optimizer owns: the never-stepped ones (classifier tail, image-bank Linears, ... SURVEY §0.4)
     # keep ACCUMULATING across steps and count toward the clip norm.  The warm-up step left one such contribution in
