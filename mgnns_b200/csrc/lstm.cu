@@ -244,6 +244,11 @@ __device__ __forceinline__ void cl_store(uint32_t addr, float v) {
 __device__ __forceinline__ void cl_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Split form.  The release of an arrive covers every earlier write of the thread, global ones included, so the
+// per-step result stores (Y / gates / c / h_prev, dG) are issued BETWEEN arrive and wait: the barrier then only
+// waits for the shared-memory exchange, and the global stores drain while the next step's product runs.
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ G, const float* __restrict__ wt_f, const float* __restrict__ wt_r,
@@ -330,6 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         }
         __syncthreads();
         float* hnext = hs + (cur ^ 1) * H * TS;
+        float sv[2][7];                                      // i, f, g, o, c, h_prev, h of the two (unit, sequence) pairs
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (!p_ok[q]) continue;
@@ -345,17 +351,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 const float og = sigmoidf_(z0[3 * Hh + uu] + z1[3 * Hh + uu] + gin[q][3]);
                 cst[q] = fg * cst[q] + ig * gg;
                 hnew = og * tanhf_(cst[q]);
-                const int64_t row = rowq[q];
-                Y[row * (2 * H) + dir * H + u] = hnew;
-                float* gs = gates + (row * 2 + dir) * (4 * H);
-                gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
-                csave[(row * 2 + dir) * H + u] = cst[q];
-                hprev[(row * 2 + dir) * H + u] = hold;
+                sv[q][0] = ig; sv[q][1] = fg; sv[q][2] = gg; sv[q][3] = og; sv[q][4] = cst[q]; sv[q][5] = hold; sv[q][6] = hnew;
             }
             hnext[u * TS + s] = hnew;
             cl_store(cl_map(hnext + u * TS + s, peer), hnew);
         }
-        cl_sync();
+        cl_arrive();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!act[q]) continue;
+            const int u = rank * Hh + p_u[q];
+            const int64_t row = rowq[q];
+            Y[row * (2 * H) + dir * H + u] = sv[q][6];
+            float* gs = gates + (row * 2 + dir) * (4 * H);
+            gs[u] = sv[q][0]; gs[H + u] = sv[q][1]; gs[2 * H + u] = sv[q][2]; gs[3 * H + u] = sv[q][3];
+            csave[(row * 2 + dir) * H + u] = sv[q][4];
+            hprev[(row * 2 + dir) * H + u] = sv[q][5];
+        }
+        cl_wait();
         cur ^= 1;
     }
 }
@@ -404,26 +417,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     // phase-2 mapping: thread (kk, quarter of the 4H gate rows)
     const int kk2 = tid % 80, jq = tid / 80;
     const bool live2 = kk2 < Hh;
+    // saved forward tensors of one time step for the thread's two (unit, sequence) pairs; the NEXT step's are fetched
+    // while this step's barrier and product run, so their L2 latency is off the per-step critical path
+    struct Saved { float ig, fg, gg, og, c, cprev, dy; int64_t row; bool on; };
+    auto fetch = [&](int t, Saved (&sv)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            sv[q].on = false;
+            if (!p_ok[q] || t < 0) continue;
+            const int s = p_s[q], u = rank * Hh + p_u[q];
+            const int len = s_len[s];
+            if (t >= len) continue;
+            const int tt = dir ? (len - 1 - t) : t;
+            const int64_t row = s_off[s] + tt;
+            const float* gs = gates + (row * 2 + dir) * (4 * H);
+            sv[q].ig = __ldg(gs + u); sv[q].fg = __ldg(gs + H + u); sv[q].gg = __ldg(gs + 2 * H + u); sv[q].og = __ldg(gs + 3 * H + u);
+            sv[q].c = __ldg(csave + (row * 2 + dir) * H + u);
+            sv[q].cprev = 0.f;
+            if (t > 0) {
+                const int64_t rp = dir ? row + 1 : row - 1;
+                sv[q].cprev = __ldg(csave + (rp * 2 + dir) * H + u);
+            }
+            sv[q].dy = __ldg(dY + row * (2 * H) + dir * H + u);
+            sv[q].row = row;
+            sv[q].on = true;
+        }
+    };
+    Saved cur_sv[2], nxt_sv[2];
+    fetch(tile_len - 1, cur_sv);
     for (int t = tile_len - 1; t >= 0; --t) {
         // ---- phase 1: gate gradients for this CTA's hidden units -------------------------------------
+        float dzq[2][4];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (!p_ok[q]) continue;
             const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
-            const int len = s_len[s];
-            float dz[4] = {0.f, 0.f, 0.f, 0.f};
-            if (t < len) {
-                const int tt = dir ? (len - 1 - t) : t;
-                const int64_t row = s_off[s] + tt;
-                const float* gs = gates + (row * 2 + dir) * (4 * H);
-                const float ig = gs[u], fg = gs[H + u], gg = gs[2 * H + u], og = gs[3 * H + u];
-                const float c = csave[(row * 2 + dir) * H + u];
-                float cprev = 0.f;
-                if (t > 0) {
-                    const int64_t rp = dir ? row + 1 : row - 1;
-                    cprev = csave[(rp * 2 + dir) * H + u];
-                }
-                const float dhv = dY[row * (2 * H) + dir * H + u] + dh[s * Hh + uu];
+            float (&dz)[4] = dzq[q];
+            dz[0] = dz[1] = dz[2] = dz[3] = 0.f;
+            if (cur_sv[q].on) {
+                const float ig = cur_sv[q].ig, fg = cur_sv[q].fg, gg = cur_sv[q].gg, og = cur_sv[q].og;
+                const float c = cur_sv[q].c, cprev = cur_sv[q].cprev;
+                const float dhv = cur_sv[q].dy + dh[s * Hh + uu];
                 const float tc = tanhf_(c);
                 const float dct = dcs[q] + dhv * og * (1.f - tc * tc);
                 dz[0] = dct * gg * ig * (1.f - ig);
@@ -431,8 +465,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 dz[2] = dct * ig * (1.f - gg * gg);
                 dz[3] = dhv * tc * og * (1.f - og);
                 dcs[q] = dct * fg;
-                float* out = dG + row * (8 * H) + dir * 4 * H;
-                out[u] = dz[0]; out[H + u] = dz[1]; out[2 * H + u] = dz[2]; out[3 * H + u] = dz[3];
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -441,7 +473,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 cl_store(cl_map(slot, peer), dz[g]);
             }
         }
-        cl_sync();
+        cl_arrive();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!p_ok[q] || !cur_sv[q].on) continue;
+            const int u = rank * Hh + p_u[q];
+            float* out = dG + cur_sv[q].row * (8 * H) + dir * 4 * H;
+            out[u] = dzq[q][0]; out[H + u] = dzq[q][1]; out[2 * H + u] = dzq[q][2]; out[3 * H + u] = dzq[q][3];
+        }
+        fetch(t - 1, nxt_sv);
+        cl_wait();
         // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
         if (t > 0) {
             float acc[TS];
@@ -467,6 +508,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 dh[i] = part[i] + part[TS * Hh + i] + part[2 * TS * Hh + i] + part[3 * TS * Hh + i];
         }
         cl_sync();      // dzs may be overwritten (also remotely) by the next step only after both CTAs finished phase 2
+#pragma unroll
+        for (int q = 0; q < 2; ++q) cur_sv[q] = nxt_sv[q];
     }
 }
 
