@@ -356,7 +356,13 @@ int mgnns_label_cooccurrence(const int32_t* labels, const int32_t* lens, int64_t
 int mgnns_sqnorm_f32(const float* g, int64_t n, double* out, void* stream);
 int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t* seg_p, const float* seg_lr,
                         const float* seg_wd, int n_seg, float* p, float* m, float* v, const double* sqnorm,
-                        float max_norm, float beta1, float beta2, float eps, const int64_t* step, void* stream);
+                        double max_norm, double beta1, double beta2, double eps, const int64_t* step, void* stream);
+
+
+/* A single-thread kernel that completes `ns` nanoseconds (<= 1 ms) after it starts: a timed dependency edge for the
+ * multi-stream training step (mgnns_b200/ops.py gates the image-bank weight-gradient kernels behind the launch of the
+ * LSTM recurrence, engine:847 loss.backward()). No reference counterpart. */
+int mgnns_delay_ns(int ns, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ that is turned into a RuntimeError carrying mgnns_last_error().
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_double, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmgnns_b200.so")
@@ -61,7 +61,8 @@ SIGNATURES = {
     "mgnns_pmi_row_reduce": (c_int, [P, P, c_int, c_int, P, P, P, P]),
     "mgnns_pmi_compact": (c_int, [P, P, P, P, c_int, P, P, P]),
     "mgnns_sqnorm_f32": (c_int, [P, c_int64, P, P]),
-    "mgnns_clip_adam_f32": (c_int, [P, c_int64, P, P, P, P, c_int, P, P, P, P, c_float, c_float, c_float, c_float, P, P]),
+    "mgnns_clip_adam_f32": (c_int, [P, c_int64, P, P, P, P, c_int, P, P, P, P, c_double, c_double, c_double, c_double, P, P]),
+    "mgnns_delay_ns": (c_int, [c_int, P]),
     "mgnns_confusion_count": (c_int, [P, c_int64, P, c_int, c_int, P, P, P]),
     "mgnns_label_cooccurrence": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),

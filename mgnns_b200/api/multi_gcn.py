@@ -16,6 +16,8 @@ from .graph_util import CSRAdjacency, as_csr, gen_A, gen_adj
 from .layers import CoAttention, MyAnotherMultiHeadAttention, MyMultiHeadAttention  # noqa: F401
 from .text_gcn import Model as Text_GCN_Model
 
+# forward schedule knob (see forward()): 1 = the scene channel's image-bank kernel waits for the last LSTM layer's launch
+_PLACE_AFTER_LAST_LAYER = os.environ.get('MGNNS_PLACE_AFTER_LAST_LAYER', '1') == '1'
 _PKG_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data', 'label_graphs.npz')
 
 # ref: models/Multi_GCN_Multihead_att.py:20-27 loads the label GloVe matrix at import time from a path
@@ -396,12 +398,14 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 text_memory_bank = text_bank(lambda: lstm_ready.append(s_txt.record_event()))
                 ev_bank = s_txt.record_event()
             with torch.cuda.stream(s_obj):
-                for ev in lstm_ready:
+                for ev in lstm_ready[:1]:
                     s_obj.wait_event(ev)
                 img_object_memory_bank, object_x_attention = object_channel()
                 ev_obj = s_obj.record_event()
             with torch.cuda.stream(s_plc):
-                for ev in lstm_ready:
+                # the scene channel's image-bank kernel is released behind the LAST layer's recurrence launch: a
+                # persistent kernel that already holds every SM would make that recurrence wait for all of it
+                for ev in (lstm_ready if _PLACE_AFTER_LAST_LAYER else lstm_ready[:1]):
                     s_plc.wait_event(ev)
                 img_place_memory_bank, place_x_attention = place_channel()
                 ev_plc = s_plc.record_event()

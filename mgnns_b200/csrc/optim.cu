@@ -48,16 +48,18 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ g, i
                                                         const int64_t* __restrict__ seg_p, const float* __restrict__ seg_lr,
                                                         const float* __restrict__ seg_wd, int n_seg,
                                                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                        const double* __restrict__ sqnorm, float max_norm, float beta1,
-                                                        float beta2, float eps, const int64_t* __restrict__ step) {
+                                                        const double* __restrict__ sqnorm, float max_norm, double beta1d,
+                                                        double beta2d, float eps, const int64_t* __restrict__ step) {
     __shared__ int64_t s_g[OPT_MAX_SEG + 1];
     for (int i = threadIdx.x; i <= n_seg; i += blockDim.x) s_g[i] = seg_g[i];
     __syncthreads();
     const float norm = (float)sqrt(*sqnorm);
     const float coef = fminf(1.f, max_norm / (norm + 1e-6f));
     const double t = (double)(*step);
-    const float bc1 = (float)(1.0 - pow((double)beta1, t));
-    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    const float bc1 = (float)(1.0 - pow(beta1d, t));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2d, t));
+    // torch forms 1 - beta in double before narrowing (1.f - 0.999f is 1.3e-5 off 0.001)
+    const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
     // every tensor starts at a multiple of 4 floats in both buffers (the host pads), so a float4 never straddles a segment
     const int64_t n4 = n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ g, i
 #define MG_ADAM(c)                                                         \
         {                                                                  \
             const float gg = gv.c + wd * pv.c;                             \
-            mv.c = mv.c + (1.f - beta1) * (gg - mv.c);                     \
-            vv.c = beta2 * vv.c + (1.f - beta2) * gg * gg;                 \
+            mv.c = mv.c + omb1 * (gg - mv.c);                              \
+            vv.c = beta2 * vv.c + omb2 * gg * gg;                          \
             pv.c -= step_size * mv.c / (sqrtf(vv.c) / bc2_sqrt + eps);     \
         }
         MG_ADAM(x) MG_ADAM(y) MG_ADAM(z) MG_ADAM(w)
@@ -93,9 +95,28 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ g, i
     }
 }
 
+// one thread that returns `ns` nanoseconds after it starts: a timed edge in the stream graph of the training step
+// (ops.py: a kernel that must start just AFTER a latency-critical one has been handed its SMs waits on the event
+// recorded behind this)
+__global__ void delay_kernel(unsigned ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+
 }  // namespace mgnns
 
 using namespace mgnns;
+
+extern "C" int mgnns_delay_ns(int ns, void* stream) {
+    MG_REQUIRE(ns >= 0 && ns <= 1000000, "delay: between 0 and 1,000,000 ns");
+    delay_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned)ns);
+    MG_LAUNCH_CHECK("delay");
+    return 0;
+}
 
 extern "C" int mgnns_sqnorm_f32(const float* g, int64_t n, double* out, void* stream) {
     MG_REQUIRE(n >= 0 && out, "sqnorm: bad argument");
@@ -113,7 +134,7 @@ extern "C" int mgnns_sqnorm_f32(const float* g, int64_t n, double* out, void* st
 
 extern "C" int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t* seg_p, const float* seg_lr,
                                    const float* seg_wd, int n_seg, float* p, float* m, float* v, const double* sqnorm,
-                                   float max_norm, float beta1, float beta2, float eps, const int64_t* step, void* stream) {
+                                   double max_norm, double beta1, double beta2, double eps, const int64_t* step, void* stream) {
     MG_REQUIRE(n >= 0 && n_seg >= 1 && n_seg <= OPT_MAX_SEG, "clip_adam: between 1 and %d segments", OPT_MAX_SEG);
     if (n == 0) return 0;
     MG_REQUIRE(g && seg_g && seg_p && seg_lr && seg_wd && p && m && v && sqnorm && step, "clip_adam: null pointer");
@@ -121,8 +142,8 @@ extern "C" int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, co
                "clip_adam: buffers must be 16-byte aligned and padded to a multiple of 4 floats");
     int blocks = (int)((n / 4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    clip_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, seg_g, seg_p, seg_lr, seg_wd, n_seg, p, m, v, sqnorm, max_norm,
-                                                           beta1, beta2, eps, step);
+    clip_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, seg_g, seg_p, seg_lr, seg_wd, n_seg, p, m, v, sqnorm,
+                                                           (float)max_norm, beta1, beta2, (float)eps, step);
     MG_LAUNCH_CHECK("clip_adam");
     return 0;
 }

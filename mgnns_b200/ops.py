@@ -96,7 +96,17 @@ class _timed:
 # enqueued on a side stream (they overlap the latency-bound recurrence of the next layer), autograd is handed None
 # for those parameters, and join_deferred() — called after loss.backward() — joins the side stream and adds the
 # results to .grad.  Opt-in (GraphedTrainStep does both); gradients are identical to the inline path.
-_defer_state = {"enabled": False, "streams": {}, "pending": []}
+#
+# "Heavy" deferred work (the image-bank weight gradients: persistent tensor-core kernels that take every SM for
+# ~0.8 ms) is additionally GATED: the latency-bound LSTM recurrence is the critical path of the backward pass, and a
+# persistent kernel that got onto the SMs first made it wait for the whole 0.8 ms.  The LSTM backward therefore drops
+# a gate event just before each recurrence launch, heavy jobs are only queued while autograd runs, and
+# join_deferred() issues job i on its own side stream behind (its inputs, gate i + a few microseconds): the
+# recurrence has been handed its SMs when the heavy kernel starts, which then fills the remaining ones.  Everything
+# is stream dependencies, so a CUDA-graph capture records exactly this order.
+_defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": []}
+_GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
+_GATE_HEAVY = os.environ.get("MGNNS_GATE_HEAVY", "1") == "1"
 
 
 def defer_weight_grads(enabled: bool) -> bool:
@@ -104,18 +114,22 @@ def defer_weight_grads(enabled: bool) -> bool:
     return prev
 
 
-def _defer_stream(device):
-    s = _defer_state["streams"].get(device)
+def _defer_stream(device, which=0):
+    s = _defer_state["streams"].get((device, which))
     if s is None:
-        s = _defer_state["streams"][device] = torch.cuda.Stream(device=device)
+        s = _defer_state["streams"][(device, which)] = torch.cuda.Stream(device=device)
     return s
 
 
-def _run_deferred(fn, inputs, params):
+def _run_deferred(fn, inputs, params, heavy=False):
     """Enqueue fn() -> list of gradient tensors (one per entry of `params`, None allowed) on the side stream, after
-    everything enqueued so far on the current stream; the (param, grad) pairs are applied by join_deferred()."""
+    everything enqueued so far on the current stream; the (param, grad) pairs are applied by join_deferred().
+    heavy=True: only queued here (with an "inputs ready" event), issued by join_deferred() behind a gate."""
     dev = inputs[0].device
     cur = torch.cuda.current_stream(dev)
+    if heavy and _GATE_HEAVY:
+        _defer_state["heavy"].append((fn, inputs, params, cur.record_event()))
+        return
     side = _defer_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
@@ -127,14 +141,48 @@ def _run_deferred(fn, inputs, params):
             _defer_state["pending"].append((p, g))
 
 
+def _drop_gate(device):
+    """Called right before a latency-critical kernel is enqueued on the current stream (deferral on): the returned
+    event fires once everything before that kernel has finished, plus _GATE_DELAY_NS on a helper stream — i.e. just
+    after the critical kernel's CTAs have been dispatched."""
+    if not (_defer_state["enabled"] and _GATE_HEAVY):
+        return
+    ev = torch.cuda.current_stream(device).record_event()
+    if _GATE_DELAY_NS > 0:
+        helper = _defer_stream(device, 'gate%d' % len(_defer_state["gates"]))
+        helper.wait_event(ev)
+        _check(_lib.mgnns_delay_ns(_GATE_DELAY_NS, helper.cuda_stream), "delay")
+        ev = helper.record_event()
+        _defer_state["gate_streams"].append((device, helper))
+    _defer_state["gates"].append(ev)
+
+
 def join_deferred():
-    """Join the deferred weight-gradient stream into the current one and accumulate the results into .grad
-    (call after loss.backward(), before anything reads the gradients)."""
+    """Issue the gated heavy jobs, join every deferred stream into the current one and accumulate the results into
+    .grad (call after loss.backward(), before anything reads the gradients)."""
+    heavy, _defer_state["heavy"] = _defer_state["heavy"], []
+    gates, _defer_state["gates"] = _defer_state["gates"], []
+    joined = set(_defer_state["gate_streams"])       # helper streams rejoin even when no heavy job waited on them
+    _defer_state["gate_streams"] = []
+    for i, (fn, inputs, params, ready) in enumerate(heavy):
+        dev = inputs[0].device
+        side = _defer_stream(dev, 'heavy%d' % (i % 2))
+        side.wait_event(ready)
+        if gates:
+            side.wait_event(gates[min(i, len(gates) - 1)])
+        with torch.cuda.stream(side):
+            grads = fn()
+        for t in inputs:
+            t.record_stream(side)
+        joined.add((dev, side))
+        for p, g in zip(params, grads):
+            if p is not None and g is not None:
+                _defer_state["pending"].append((p, g))
     pending, _defer_state["pending"] = _defer_state["pending"], []
-    devs = {g.device for _, g in pending}
-    for dev in devs:
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_stream(_defer_stream(dev))
+    for dev in {g.device for _, g in pending}:
+        joined.add((dev, _defer_stream(dev)))
+    for dev, side in joined:
+        torch.cuda.current_stream(dev).wait_stream(side)
     for p, g in pending:
         g.record_stream(torch.cuda.current_stream(g.device))
         if p.grad is None:
@@ -980,6 +1028,7 @@ def _imgbank_setup(ctx, inputs, output):
     fmap, weight, bias = inputs
     ctx.save_for_backward(fmap, weight, output[2])
     ctx.fshape = fmap.shape
+    ctx.leaves = (weight, bias)            # the parameter objects themselves (deferred weight gradients)
 
 
 def _pick_reduce(batch, target=32):
@@ -997,19 +1046,30 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
     g_f = g_w = g_b = None
     if g_bank is not None:
         g_bank = _f32c(g_bank, "grad_bank")
-    if ctx.needs_input_grad[1] and g_bank is not None:
-        # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
-        g_w = torch.zeros_like(weight)
-        r = _pick_reduce(B)
-        if _tc_ok(C, P, O, 320):
-            with _timed("imgbank_dw"):
-                _check(_lib.mgnns_imgbank_dw_tc(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
-                                                _PRECISIONS[_precision], g_w.data_ptr(), _stream()), "imgbank_dw_tc")
-        else:
-          with _timed("imgbank_dw"):
-            gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, g_w, C, 0, batch=B, reduce=r, accumulate=1)
-    if ctx.needs_input_grad[2] and g_bank is not None:
-        g_b = colsum(g_bank.reshape(B * P, O))
+    need_w, need_b = ctx.needs_input_grad[1] and g_bank is not None, ctx.needs_input_grad[2] and g_bank is not None
+
+    def weight_grads():
+        gw = gb = None
+        if need_w:
+            # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
+            gw = torch.zeros_like(weight)
+            r = _pick_reduce(B)
+            if _tc_ok(C, P, O, 320):
+                with _timed("imgbank_dw"):
+                    _check(_lib.mgnns_imgbank_dw_tc(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
+                                                    _PRECISIONS[_precision], gw.data_ptr(), _stream()), "imgbank_dw_tc")
+            else:
+                with _timed("imgbank_dw"):
+                    gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, gw, C, 0, batch=B, reduce=r, accumulate=1)
+        if need_b:
+            gb = colsum(g_bank.reshape(B * P, O))
+        return [gw, gb]
+
+    if (need_w or need_b) and _defer_state["enabled"] and all(p.is_leaf for p in ctx.leaves):
+        # not needed before the optimizer: leaves the backward chain (and is gated behind the LSTM recurrence)
+        _run_deferred(weight_grads, (g_bank, fmap3), ctx.leaves, heavy=True)
+    elif need_w or need_b:
+        g_w, g_b = weight_grads()
     if ctx.needs_input_grad[0]:
         g_f = torch.empty_like(fmap3) if g_bank is not None else torch.zeros_like(fmap3)
         if g_bank is not None:
@@ -1298,6 +1358,7 @@ def _lstm_backward(ctx, gy, ggates, gc, ghp):
     gy = _f32c(gy, "grad_y")
     N = gy.shape[0]
     dG = torch.zeros((N, 8 * H), device=gy.device, dtype=torch.float32)
+    _drop_gate(gy.device)                  # gated heavy jobs (image-bank weight gradients) start just behind this launch
     with _timed("lstm_rec_bwd"):
         _check(_lib.mgnns_lstm_rec_bwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), ctx.n_tiles, H,
                                        gy.data_ptr(), gates.data_ptr(), csave.data_ptr(), whh_f.data_ptr(),
@@ -1385,8 +1446,10 @@ def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, 
         _need_cuda(x)
         x = _f32c(x, "x")
         g = _LstmInputProjection.apply(x, P("weight_ih"), R("weight_ih"), *biases)                  # [N, 8H]
-        if layer == 0 and after_first_projection is not None:
-            after_first_projection()      # e.g. record an event: the (SM-hungry) recurrence is about to be enqueued
+        if after_first_projection is not None:
+            # called once per layer, just before its (latency-critical, SM-hungry) recurrence is enqueued — e.g. to
+            # record an event that releases a persistent kernel of another stream behind this launch
+            after_first_projection()
         y = torch.ops.mgnns.lstm_rec(g, P("weight_hh"), R("weight_hh"), plan.offsets, plan.lens, plan.tiles, plan.n_tiles)[0]
         if layer + 1 < lstm.num_layers and training and lstm.dropout > 0:
             y = torch.nn.functional.dropout(y, lstm.dropout, True)
