@@ -271,6 +271,10 @@ int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bi
                          float* bank, void* stream);
 int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O,
                         int precision, float* gW, void* stream);
+/* same, on at most max_ctas SMs (0 = all): the weight gradient is not needed before the optimizer (engine:850-851), so
+ * the training step runs it beside the latency-bound backward chain instead of in front of it */
+int mgnns_imgbank_dw_tc_capped(const float* fmap, const float* gbank, int B, int C, int P, int O,
+                               int precision, float* gW, int max_ctas, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Length-aware bidirectional LSTM recurrence over compacted tokens (PyTorch gate order i,f,g,o).

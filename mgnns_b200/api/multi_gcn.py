@@ -291,6 +291,11 @@ class Multi_GCN_Multihead_Att(nn.Module):
 
     def _img_bank(self, feats, linear):
         bank, pooled, _ = torch.ops.mgnns.imgbank(feats, linear.weight, linear.bias)
+        if not feats.requires_grad:
+            # pooled depends on the feature map only: with frozen / absent trunks nothing upstream wants its gradient,
+            # and leaving it attached would make the image-bank backward (the weight gradient) wait for the whole
+            # label-channel backward to deliver a gradient nobody reads
+            pooled = pooled.detach()
         return bank, pooled
 
     def get_img_object_memory_bank(self, img_object_feats):

@@ -468,7 +468,8 @@ __global__ void split_weight_tf32_kernel(const float* __restrict__ w, float* __r
 }
 
 template <int PROBLEM, bool SPLIT>
-static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& blo, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& blo, const Params& p, cudaStream_t st,
+                  int max_ctas = 0) {
     using CF = Cfg<PROBLEM, SPLIT>;
     static bool configured = false;
     if (!configured) {
@@ -479,6 +480,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap&
         configured = true;
     }
     int grid = tc_grid_limit();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > p.n_items) grid = p.n_items;
     Params q = p;
     q.counter = next_tile_counter(st);
@@ -559,6 +561,13 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
 // gW[O,C] += sum_b gbank_b^T . fmap_b^T   (gW must be initialised by the caller)
 extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O, int precision,
                                    float* gW, void* stream) {
+    return mgnns_imgbank_dw_tc_capped(fmap, gbank, B, C, P, O, precision, gW, 0, stream);
+}
+
+// max_ctas > 0 caps the persistent grid (the dynamic tile scheduler makes the grid size a free parameter): a weight
+// gradient that is off the critical path can run on a share of the SMs and leave the rest to the latency-bound chain
+extern "C" int mgnns_imgbank_dw_tc_capped(const float* fmap, const float* gbank, int B, int C, int P, int O, int precision,
+                                          float* gW, int max_ctas, void* stream) {
     MG_REQUIRE(B >= 0 && C >= 1 && P >= 1 && O >= 1, "imgbank_dw_tc: bad dimensions");
     MG_REQUIRE(O <= Geo<DW>::BN && O % 4 == 0, "imgbank_dw_tc: O=%d must be <= 320 and a multiple of 4", O);
     MG_REQUIRE(P % 4 == 0, "imgbank_dw_tc: P=%d must be a multiple of 4 (16-byte TMA strides)", P);
@@ -593,5 +602,5 @@ extern "C" int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B,
     p.pooled_ord = nullptr;
     p.n_items = c_tiles * groups;
     cudaStream_t st = as_stream(stream);
-    return precision ? launch<DW, true>(ma, mb, mb, p, st) : launch<DW, false>(ma, mb, mb, p, st);
+    return precision ? launch<DW, true>(ma, mb, mb, p, st, max_ctas) : launch<DW, false>(ma, mb, mb, p, st, max_ctas);
 }

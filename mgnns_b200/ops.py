@@ -107,6 +107,9 @@ class _timed:
 _defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": []}
 _GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
 _GATE_HEAVY = os.environ.get("MGNNS_GATE_HEAVY", "1") == "1"
+# > 0: heavy jobs are instead issued at once on their own stream with the persistent grid capped to this many CTAs
+# (static SM partition: the rest of the GPU stays free for the critical chain)
+_HEAVY_CTAS = int(os.environ.get("MGNNS_HEAVY_CTAS", "0"))
 
 
 def defer_weight_grads(enabled: bool) -> bool:
@@ -127,10 +130,15 @@ def _run_deferred(fn, inputs, params, heavy=False):
     heavy=True: only queued here (with an "inputs ready" event), issued by join_deferred() behind a gate."""
     dev = inputs[0].device
     cur = torch.cuda.current_stream(dev)
-    if heavy and _GATE_HEAVY:
+    if heavy and _HEAVY_CTAS <= 0 and _GATE_HEAVY:
         _defer_state["heavy"].append((fn, inputs, params, cur.record_event()))
         return
-    side = _defer_stream(dev)
+    if heavy and _HEAVY_CTAS > 0:
+        _defer_state["n_early"] = _defer_state.get("n_early", 0) + 1
+        side = _defer_stream(dev, 'heavy%d' % (_defer_state["n_early"] % 2))
+        _defer_state["gate_streams"].append((dev, side))          # joined by join_deferred()
+    else:
+        side = _defer_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         grads = fn()
@@ -188,7 +196,10 @@ def join_deferred():
         if p.grad is None:
             p.grad = g
         else:
-            p.grad = p.grad + g
+            # in place, as AccumulateGrad does: a never-stepped parameter keeps ONE gradient buffer that accumulates
+            # across steps, and a captured graph must keep writing to that same buffer on every replay
+            with torch.no_grad():
+                p.grad.add_(g)
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -1048,7 +1059,7 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
         g_bank = _f32c(g_bank, "grad_bank")
     need_w, need_b = ctx.needs_input_grad[1] and g_bank is not None, ctx.needs_input_grad[2] and g_bank is not None
 
-    def weight_grads():
+    def weight_grads(max_ctas=0):
         gw = gb = None
         if need_w:
             # gW [O,C] = sum_b gbank_b^T [O,P] @ fmap_b^T [P,C]
@@ -1056,8 +1067,9 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
             r = _pick_reduce(B)
             if _tc_ok(C, P, O, 320):
                 with _timed("imgbank_dw"):
-                    _check(_lib.mgnns_imgbank_dw_tc(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
-                                                    _PRECISIONS[_precision], gw.data_ptr(), _stream()), "imgbank_dw_tc")
+                    _check(_lib.mgnns_imgbank_dw_tc_capped(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
+                                                           _PRECISIONS[_precision], gw.data_ptr(), max_ctas, _stream()),
+                           "imgbank_dw_tc")
             else:
                 with _timed("imgbank_dw"):
                     gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, gw, C, 0, batch=B, reduce=r, accumulate=1)
@@ -1067,7 +1079,8 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
 
     if (need_w or need_b) and _defer_state["enabled"] and all(p.is_leaf for p in ctx.leaves):
         # not needed before the optimizer: leaves the backward chain (and is gated behind the LSTM recurrence)
-        _run_deferred(weight_grads, (g_bank, fmap3), ctx.leaves, heavy=True)
+        _run_deferred((lambda: weight_grads(_HEAVY_CTAS)) if _HEAVY_CTAS > 0 else weight_grads, (g_bank, fmap3), ctx.leaves,
+                      heavy=True)
     elif need_w or need_b:
         g_w, g_b = weight_grads()
     if ctx.needs_input_grad[0]:

