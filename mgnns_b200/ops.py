@@ -107,6 +107,7 @@ class _timed:
 _defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": []}
 _GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
 _GATE_HEAVY = os.environ.get("MGNNS_GATE_HEAVY", "1") == "1"
+_DEFER_SMALL = os.environ.get("MGNNS_DEFER_SMALL", "1") == "1"     # also defer the small (M = batch) weight gradients
 # > 0: heavy jobs are instead issued at once on their own stream with the persistent grid capped to this many CTAs
 # (static SM partition: the rest of the GPU stays free for the critical chain)
 _HEAVY_CTAS = int(os.environ.get("MGNNS_HEAVY_CTAS", "0"))
@@ -136,9 +137,10 @@ def _run_deferred(fn, inputs, params, heavy=False):
     if heavy and _HEAVY_CTAS > 0:
         _defer_state["n_early"] = _defer_state.get("n_early", 0) + 1
         side = _defer_stream(dev, 'heavy%d' % (_defer_state["n_early"] % 2))
-        _defer_state["gate_streams"].append((dev, side))          # joined by join_deferred()
     else:
-        side = _defer_stream(dev)
+        # one side stream per origin stream: the four attention stacks' weight gradients do not queue behind each other
+        side = _defer_stream(dev, ('side', cur.cuda_stream))
+    _defer_state["gate_streams"].append((dev, side))              # joined by join_deferred()
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         grads = fn()
@@ -187,8 +189,6 @@ def join_deferred():
             if p is not None and g is not None:
                 _defer_state["pending"].append((p, g))
     pending, _defer_state["pending"] = _defer_state["pending"], []
-    for dev in {g.device for _, g in pending}:
-        joined.add((dev, _defer_stream(dev)))
     for dev, side in joined:
         torch.cuda.current_stream(dev).wait_stream(side)
     for p, g in pending:
@@ -402,6 +402,7 @@ def _mm_setup(ctx, inputs, output):
     a, b, bias, trans_a, trans_b, act, slope = inputs
     ctx.save_for_backward(a, b, output if act != ACT_NONE else None)
     ctx.cfg = (trans_a, trans_b, act, slope, bias is not None)
+    ctx.leaves = (b, bias)                 # the parameter objects themselves (deferred weight gradients)
 
 
 def _mm_backward(ctx, g):
@@ -412,10 +413,23 @@ def _mm_backward(ctx, g):
     mm = _mm_impl            # backward needs no autograd graph: skip the dispatcher
     if ctx.needs_input_grad[0]:
         ga = mm(g, b, None, False, not tb, ACT_NONE, 0.0) if not ta else mm(b, g, None, tb, True, ACT_NONE, 0.0)
-    if ctx.needs_input_grad[1]:
-        gb = mm(a, g, None, not ta, False, ACT_NONE, 0.0) if not tb else mm(g, a, None, True, ta, ACT_NONE, 0.0)
-    if has_bias and ctx.needs_input_grad[2]:
-        gbias = colsum(g)
+    need_w, need_bias = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+
+    def weight_grads():
+        gw_ = gbias_ = None
+        if need_w:
+            gw_ = mm(a, g, None, not ta, False, ACT_NONE, 0.0) if not tb else mm(g, a, None, True, ta, ACT_NONE, 0.0)
+        if need_bias:
+            gbias_ = colsum(g)
+        return [gw_, gbias_]
+
+    w_leaf, bias_leaf = ctx.leaves
+    if ((need_w or need_bias) and _defer_state["enabled"] and _DEFER_SMALL and w_leaf.is_leaf
+            and (bias_leaf is None or bias_leaf.is_leaf)):
+        # a parameter's gradient is not needed before the optimizer: off the backward chain, onto the side stream
+        _run_deferred(weight_grads, (g, a), (w_leaf if need_w else None, bias_leaf if need_bias else None))
+    elif need_w or need_bias:
+        gb, gbias = weight_grads()
     return ga, gb, gbias, None, None, None, None
 
 
@@ -478,6 +492,7 @@ def _head_mm_setup(ctx, inputs, output):
     x, w, heads, mode = inputs
     ctx.save_for_backward(x, w)
     ctx.cfg = (heads, mode)
+    ctx.leaves = (w,)
 
 
 def _head_mm_backward(ctx, g):
@@ -491,12 +506,19 @@ def _head_mm_backward(ctx, g):
     gx = gw = None
     if ctx.needs_input_grad[0]:
         gx = torch.ops.mgnns.head_mm(g, w, heads, 1 - mode)
-    if ctx.needs_input_grad[1]:
-        gw = torch.empty_like(w)
+    def weight_grads():
+        gw_ = torch.empty_like(w)
         if mode == 0:   # gw_h [dk, D] = x_h^T @ g_h
-            gemm_raw(1, 0, dk, D, B, x, heads * dk, dk, g, heads * D, D, gw, D, dk * D, batch=heads)
+            gemm_raw(1, 0, dk, D, B, x, heads * dk, dk, g, heads * D, D, gw_, D, dk * D, batch=heads)
         else:           # gw_h [dv, D] = g_h^T @ x_h
-            gemm_raw(1, 0, dk, D, B, g, heads * dk, dk, x, heads * D, D, gw, D, dk * D, batch=heads)
+            gemm_raw(1, 0, dk, D, B, g, heads * dk, dk, x, heads * D, D, gw_, D, dk * D, batch=heads)
+        return [gw_]
+
+    if ctx.needs_input_grad[1]:
+        if _defer_state["enabled"] and _DEFER_SMALL and ctx.leaves[0].is_leaf:
+            _run_deferred(weight_grads, (g, x), ctx.leaves)
+        else:
+            gw = weight_grads()[0]
     return gx, gw, None, None
 
 
