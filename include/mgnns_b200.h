@@ -363,6 +363,28 @@ int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t
                         double max_norm, double beta1, double beta2, double eps, const int64_t* step, void* stream);
 
 
+/* ---------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (one kernel, capturable in a CUDA graph).
+ * ref: SURVEY 8e / engine/Multi_GCN_Multihead_Att_engine.py:847-851 — the one collective of the path sits between
+ * loss.backward() and clip_grad_norm_; the reference itself is single-GPU.
+ *   mgnns_p2p_alloc / _free       cudaMalloc'd, zeroed memory that CUDA IPC can export (the flat gradient buffer and a
+ *                                 flag block of mgnns_p2p_flag_bytes() bytes per rank)
+ *   mgnns_p2p_export / _import    64-byte cudaIpcMemHandle_t of an allocation / peer mapping of another rank's handle
+ *   mgnns_allreduce_p2p_f32       buf_r[i] = scale * sum_q buf_q[i] on every rank r (bit-identical results on all
+ *                                 ranks); bufs / flags are HOST arrays of `world` device pointers, own allocation at
+ *                                 index `rank`; n % 4 == 0; all ranks must launch it the same number of times
+ *   mgnns_p2p_error               1 if a cross-GPU barrier of this rank ever timed out (4 s), -1 on a CUDA error
+ * ------------------------------------------------------------------------- */
+int mgnns_p2p_flag_bytes(void);
+int mgnns_p2p_alloc(int64_t bytes, void** out);
+int mgnns_p2p_free(void* p);
+int mgnns_p2p_export(void* p, void* handle64);
+int mgnns_p2p_import(const void* handle64, void** out);
+int mgnns_p2p_close(void* p);
+int mgnns_allreduce_p2p_f32(const uint64_t* bufs, const uint64_t* flags, int rank, int world, int64_t n,
+                            float scale, int ctas, void* stream);
+int mgnns_p2p_error(const void* own_flags, void* stream);
+
 /* A single-thread kernel that completes `ns` nanoseconds (<= 1 ms) after it starts: a timed dependency edge for the
  * multi-stream training step (mgnns_b200/ops.py gates the image-bank weight-gradient kernels behind the launch of the
  * LSTM recurrence, engine:847 loss.backward()). No reference counterpart. */

@@ -63,6 +63,14 @@ SIGNATURES = {
     "mgnns_sqnorm_f32": (c_int, [P, c_int64, P, P]),
     "mgnns_clip_adam_f32": (c_int, [P, c_int64, P, P, P, P, c_int, P, P, P, P, c_double, c_double, c_double, c_double, P, P]),
     "mgnns_delay_ns": (c_int, [c_int, P]),
+    "mgnns_p2p_flag_bytes": (c_int, []),
+    "mgnns_p2p_alloc": (c_int, [c_int64, P]),
+    "mgnns_p2p_free": (c_int, [P]),
+    "mgnns_p2p_export": (c_int, [P, P]),
+    "mgnns_p2p_import": (c_int, [P, P]),
+    "mgnns_p2p_close": (c_int, [P]),
+    "mgnns_allreduce_p2p_f32": (c_int, [P, P, c_int, c_int, c_int64, c_float, c_int, P]),
+    "mgnns_p2p_error": (c_int, [P, P]),
     "mgnns_confusion_count": (c_int, [P, c_int64, P, c_int, c_int, P, P, P]),
     "mgnns_label_cooccurrence": (c_int, [P, P, c_int64, c_int, c_int, P, P, P]),
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),

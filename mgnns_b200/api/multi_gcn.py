@@ -375,7 +375,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 x = layer(q=x, k=bank, v=bank, mask=mask)[0]
             return x
 
-        streams = self._branch_streams(3)
+        streams = self._branch_streams(5)
         if streams is None:
             # one stream, the reference's order (ref: model:444-546)
             text_feature = text_gcn()
@@ -391,8 +391,11 @@ class Multi_GCN_Multihead_Att(nn.Module):
             # each need two of them.  Every chain stays on its own stream and waits only for the tensor it needs
             # (events), so e.g. the image-query stacks overlap the LSTM.  Autograd replays each backward op on its
             # forward stream, so the backward pass forks the same way; a CUDA-graph capture records parallel paths.
-            main, (s_txt, s_obj, s_plc) = streams
-            for side in (s_txt, s_obj, s_plc):
+            # The label-graph half of an image channel (pooled -> label GCN scores -> label attention) has its own
+            # stream: in the backward pass it is fed late (through the text-bank stacks), and on a shared stream it
+            # would sit in front of the image-bank weight gradient, which is ready much earlier.
+            main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab) = streams
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab):
                 side.wait_stream(main)                      # fork: after everything already enqueued on main
             # The LSTM recurrence is latency-bound and leaves most SMs idle, while the image-bank kernels are
             # persistent and take every SM they can get: the image channels therefore start once the LSTM's first
@@ -402,18 +405,31 @@ class Multi_GCN_Multihead_Att(nn.Module):
             with torch.cuda.stream(s_txt):
                 text_memory_bank = text_bank(lambda: lstm_ready.append(s_txt.record_event()))
                 ev_bank = s_txt.record_event()
-            with torch.cuda.stream(s_obj):
-                for ev in lstm_ready[:1]:
-                    s_obj.wait_event(ev)
-                img_object_memory_bank, object_x_attention = object_channel()
-                ev_obj = s_obj.record_event()
-            with torch.cuda.stream(s_plc):
-                # the scene channel's image-bank kernel is released behind the LAST layer's recurrence launch: a
-                # persistent kernel that already holds every SM would make that recurrence wait for all of it
-                for ev in (lstm_ready if _PLACE_AFTER_LAST_LAYER else lstm_ready[:1]):
-                    s_plc.wait_event(ev)
-                img_place_memory_bank, place_x_attention = place_channel()
-                ev_plc = s_plc.record_event()
+
+            def image_channel(s_img, s_lab, gates, trunk, feature, linear, inp, adj, attention, linear_5, x_linear, attr):
+                with torch.cuda.stream(s_img):
+                    for ev in gates:
+                        s_img.wait_event(ev)
+                    fmap = trunk(feature)
+                    setattr(self, attr, fmap)                                         # side-effect attrs of the reference
+                    bank, pooled = self._img_bank(fmap, linear)
+                    ev_img = s_img.record_event()
+                with torch.cuda.stream(s_lab):
+                    s_lab.wait_event(ev_img)
+                    x_att = self._label_channel(pooled, inp, adj, attention, linear_5, x_linear, query)
+                    ev_lab = s_lab.record_event()
+                pooled.record_stream(s_lab)
+                return bank, x_att, ev_lab
+
+            # the scene channel's image-bank kernel is released behind the LAST layer's recurrence launch: a
+            # persistent kernel that already holds every SM would make that recurrence wait for all of it
+            img_object_memory_bank, object_x_attention, ev_obj = image_channel(
+                s_obj, s_obj_lab, lstm_ready[:1], self.object_features, object_feature, self.liner_img_object, object_inp,
+                'object_A', self.object_attention, self.object_linear_5, self.object_x_linear, 'object_feature')
+            img_place_memory_bank, place_x_attention, ev_plc = image_channel(
+                s_plc, s_plc_lab, lstm_ready if _PLACE_AFTER_LAST_LAYER else lstm_ready[:1], self.place_features,
+                place_feature, self.liner_img_place, place_inp, 'place_A', self.place_attention, self.place_linear_5,
+                self.place_x_linear, 'place_feature')
             text_feature = text_gcn()
             ev_tf = main.record_event()
             with torch.cuda.stream(s_obj):
@@ -429,13 +445,13 @@ class Multi_GCN_Multihead_Att(nn.Module):
             main.wait_event(ev_bank)
             main.wait_event(ev_plc)
             img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask)
-            for side in (s_txt, s_obj, s_plc):
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab):
                 main.wait_stream(side)                      # join
             # tensors that crossed streams: tell the caching allocator about every stream that read them
             for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt,)),
                                (text_memory_bank, (main,)), (place_x_attention, (main,)),
                                (text_img_object, (main,)), (text_img_place, (main,)), (img_object_text, (main,)),
-                               (text_mask, (s_txt,))):
+                               (text_mask, (s_txt,)), (query, (s_obj_lab, s_plc_lab))):
                 for r in readers:
                     t.record_stream(r)
 

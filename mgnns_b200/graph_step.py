@@ -8,10 +8,16 @@ captured graph removes that.  What makes the step capturable:
   * dropout seeds come from a device-resident counter advanced inside the graph (ops.set_seed_tensor);
   * the optimizer is constructed with capturable=True.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
+
+# world > 1: 1 (default) = the gradient all-reduce is mgnns_allreduce_p2p_f32, one kernel over NVLink peer memory INSIDE
+# the captured graph (one graph launch per step); 0 = NCCL all-reduce issued eagerly between two captured halves
+_P2P_ALLREDUCE = os.environ.get("MGNNS_P2P_ALLREDUCE", "1") == "1"
 
 
 class GraphedTrainStep:
@@ -46,6 +52,7 @@ class GraphedTrainStep:
         self.recaptures = 0
         self.time_allreduce = False
         self.allreduce_events = []
+        self.use_p2p = world_size > 1 and _P2P_ALLREDUCE
         self._capture(warmup)
 
     def _capture(self, warmup):
@@ -62,7 +69,8 @@ class GraphedTrainStep:
         ops.KernelTimers.enabled = set()
         try:
             self.graph = torch.cuda.CUDAGraph()
-            if self.world == 1:
+            if self.world == 1 or self.use_p2p:
+                # one graph: with the peer-memory all-reduce the collective is just another kernel node
                 with torch.cuda.graph(self.graph):
                     self.loss = self._step()
                     self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
@@ -88,12 +96,31 @@ class GraphedTrainStep:
         from .optim import FlatGradients
         if self._fg is None:
             fo = self.flat_opt if (self.flat_opt is not None and self.flat_opt is not True) else None
-            self._fg = fo.grads if fo is not None else FlatGradients(self.model.parameters())
+            if fo is not None:
+                self._fg = fo.grads
+            elif self.use_p2p:
+                from .p2p import PeerAllReduce
+                dev = self.batch['text'].device
+                made = []
+
+                def alloc(n):
+                    made.append(PeerAllReduce(n, dev))       # rendezvous: every rank gets here in its first step
+                    return made[0].flat
+                self._fg = FlatGradients(self.model.parameters(), alloc=alloc)
+                self._fg.peer = made[0]
+            else:
+                self._fg = FlatGradients(self.model.parameters())
             self._flat, self._views = self._fg.flat, self._fg.views
         self._fg.pack()
 
     def _allreduce(self):
-        """The one collective of the step: flat NCCL all-reduce of the gradients (SUM; the / world follows)."""
+        """The one collective of the step: all-reduce of the flat gradient buffer — the peer-memory kernel (mean, in
+        place) or NCCL (SUM; the / world follows)."""
+        if self.use_p2p:
+            if self._fg.peer is None:
+                raise RuntimeError("GraphedTrainStep: the shared FlatGradients buffer is not peer-mapped")
+            self._fg.peer.all_reduce_(1.0 / self.world)
+            return
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
 
     def _forward_backward(self):
@@ -125,7 +152,8 @@ class GraphedTrainStep:
             self._pack_grads()
         if self.world > 1:
             self._allreduce()
-            self._flat.div_(self.world)
+            if not self.use_p2p:
+                self._flat.div_(self.world)
         self._clip_and_step()
         return loss
 
@@ -141,7 +169,7 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             self.lens_key.copy_(lens_cpu)                  # in-place: bumps the version, so the plan cache misses on purpose
             self.plan = self.model.make_text_plan(self.lens_key, L, capacity=cap)
-            if self.flat_opt is None:
+            if self.flat_opt is None and not self.use_p2p:      # (a peer-mapped buffer is kept: making one is a collective)
                 self._flat, self._views, self._fg = None, None, None
                 for p in self.model.parameters():
                     p.grad = None
@@ -152,7 +180,7 @@ class GraphedTrainStep:
 
     def replay(self):
         self.graph.replay()
-        if self.world > 1:
+        if self.world > 1 and not self.use_p2p:
             if self.time_allreduce:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

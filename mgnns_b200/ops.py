@@ -10,6 +10,7 @@ Every op here:
 """
 import math
 import os
+import re
 from typing import List, Optional, Tuple
 
 import torch
@@ -106,11 +107,24 @@ class _timed:
 # is stream dependencies, so a CUDA-graph capture records exactly this order.
 _defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": []}
 _GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
-_GATE_HEAVY = os.environ.get("MGNNS_GATE_HEAVY", "1") == "1"
 _DEFER_SMALL = os.environ.get("MGNNS_DEFER_SMALL", "1") == "1"     # also defer the small (M = batch) weight gradients
-# > 0: heavy jobs are instead issued at once on their own stream with the persistent grid capped to this many CTAs
-# (static SM partition: the rest of the GPU stays free for the critical chain)
-_HEAVY_CTAS = int(os.environ.get("MGNNS_HEAVY_CTAS", "0"))
+
+
+def _parse_heavy_plan(text):
+    """"g0,g1" -> [(0 CTAs = full grid, gate 0), (0, gate 1)]; "c100,g0" -> job 0 at once on <= 100 CTAs, job 1 behind
+    gate 0; "off" -> heavy jobs run inline.  Jobs beyond the list reuse its last entry."""
+    if text.strip() == "off":
+        return None
+    plan = []
+    for spec in text.split(","):
+        m = re.fullmatch(r"(?:c(\d+))?(?:g(\d+))?", spec.strip())
+        if m is None:
+            raise ValueError("MGNNS_HEAVY_PLAN: bad entry %r" % spec)
+        plan.append((int(m.group(1) or 0), int(m.group(2)) if m.group(2) is not None else -1))
+    return plan
+
+
+_HEAVY_PLAN = _parse_heavy_plan(os.environ.get("MGNNS_HEAVY_PLAN", "g0,g1"))
 
 
 def defer_weight_grads(enabled: bool) -> bool:
@@ -128,18 +142,15 @@ def _defer_stream(device, which=0):
 def _run_deferred(fn, inputs, params, heavy=False):
     """Enqueue fn() -> list of gradient tensors (one per entry of `params`, None allowed) on the side stream, after
     everything enqueued so far on the current stream; the (param, grad) pairs are applied by join_deferred().
-    heavy=True: only queued here (with an "inputs ready" event), issued by join_deferred() behind a gate."""
+    heavy=True: fn takes the CTA cap of its persistent kernel; only queued here (with an "inputs ready" event) and
+    issued by join_deferred() as _HEAVY_PLAN says."""
     dev = inputs[0].device
     cur = torch.cuda.current_stream(dev)
-    if heavy and _HEAVY_CTAS <= 0 and _GATE_HEAVY:
+    if heavy:
         _defer_state["heavy"].append((fn, inputs, params, cur.record_event()))
         return
-    if heavy and _HEAVY_CTAS > 0:
-        _defer_state["n_early"] = _defer_state.get("n_early", 0) + 1
-        side = _defer_stream(dev, 'heavy%d' % (_defer_state["n_early"] % 2))
-    else:
-        # one side stream per origin stream: the four attention stacks' weight gradients do not queue behind each other
-        side = _defer_stream(dev, ('side', cur.cuda_stream))
+    # one side stream per origin stream: the four attention stacks' weight gradients do not queue behind each other
+    side = _defer_stream(dev, ('side', cur.cuda_stream))
     _defer_state["gate_streams"].append((dev, side))              # joined by join_deferred()
     side.wait_stream(cur)
     with torch.cuda.stream(side):
@@ -155,7 +166,7 @@ def _drop_gate(device):
     """Called right before a latency-critical kernel is enqueued on the current stream (deferral on): the returned
     event fires once everything before that kernel has finished, plus _GATE_DELAY_NS on a helper stream — i.e. just
     after the critical kernel's CTAs have been dispatched."""
-    if not (_defer_state["enabled"] and _GATE_HEAVY):
+    if not (_defer_state["enabled"] and _HEAVY_PLAN):
         return
     ev = torch.cuda.current_stream(device).record_event()
     if _GATE_DELAY_NS > 0:
@@ -178,10 +189,11 @@ def join_deferred():
         dev = inputs[0].device
         side = _defer_stream(dev, 'heavy%d' % (i % 2))
         side.wait_event(ready)
-        if gates:
-            side.wait_event(gates[min(i, len(gates) - 1)])
+        max_ctas, gate = _HEAVY_PLAN[min(i, len(_HEAVY_PLAN) - 1)]
+        if gates and gate >= 0:
+            side.wait_event(gates[min(gate, len(gates) - 1)])
         with torch.cuda.stream(side):
-            grads = fn()
+            grads = fn(max_ctas)
         for t in inputs:
             t.record_stream(side)
         joined.add((dev, side))
@@ -1099,10 +1111,9 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
             gb = colsum(g_bank.reshape(B * P, O))
         return [gw, gb]
 
-    if (need_w or need_b) and _defer_state["enabled"] and all(p.is_leaf for p in ctx.leaves):
+    if (need_w or need_b) and _defer_state["enabled"] and _HEAVY_PLAN and all(p.is_leaf for p in ctx.leaves):
         # not needed before the optimizer: leaves the backward chain (and is gated behind the LSTM recurrence)
-        _run_deferred((lambda: weight_grads(_HEAVY_CTAS)) if _HEAVY_CTAS > 0 else weight_grads, (g_bank, fmap3), ctx.leaves,
-                      heavy=True)
+        _run_deferred(weight_grads, (g_bank, fmap3), ctx.leaves, heavy=True)
     elif need_w or need_b:
         g_w, g_b = weight_grads()
     if ctx.needs_input_grad[0]:

@@ -27,7 +27,9 @@ class FlatGradients:
     tensor starting at a multiple of 4 floats); after pack() every p.grad aliases its slice, so the NCCL all-reduce,
     the clip and the optimizer all work on the same memory."""
 
-    def __init__(self, params):
+    def __init__(self, params, alloc=None):
+        """alloc(numel) -> float32 tensor of that many zeros: lets the buffer live in peer-mapped memory
+        (mgnns_b200.p2p.PeerAllReduce) so that the all-reduce is a kernel over NVLink on this very buffer."""
         self.params = [p for p in params if p.grad is not None]
         if not self.params:
             raise RuntimeError("FlatGradients: run one backward pass first (parameters without a gradient are left out)")
@@ -36,7 +38,10 @@ class FlatGradients:
             self.offsets.append(off)
             off += _pad4(p.numel())
         dev = self.params[0].device
-        self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(off, device=dev, dtype=torch.float32) if alloc is None else alloc(off)
+        if self.flat.numel() != off or self.flat.dtype != torch.float32 or self.flat.device != dev:
+            raise RuntimeError("FlatGradients: alloc() must return %d float32 elements on %s" % (off, dev))
+        self.peer = None            # set by the owner when the buffer is a PeerAllReduce's
         self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
 
     def pack(self):
