@@ -25,7 +25,7 @@
 namespace mgnns {
 
 constexpr int P2P_MAX_WORLD = 8;
-constexpr int P2P_MAX_CTAS = 64;
+constexpr int P2P_MAX_CTAS = 128;
 constexpr int P2P_THREADS = 512;
 // layout of a rank's flag allocation (uint32 words)
 constexpr int P2P_FLAG_WORDS = P2P_MAX_CTAS * P2P_MAX_WORLD;     // flag[c][peer]
@@ -79,7 +79,9 @@ __device__ __forceinline__ void p2p_barrier(const P2PParams& p, int c, uint32_t 
     __syncthreads();
 }
 
-template <int W>
+// U elements per thread and iteration: (W-1)*U remote 128-bit loads in flight per thread.  A peer load takes 1-3 us
+// under load, so NVLink bandwidth is bought with bytes in flight: ~100 CTAs x 512 threads x ~10 loads x 16 B = 8 MB.
+template <int W, int U>
 __global__ void __launch_bounds__(P2P_THREADS) allreduce_p2p_kernel(P2PParams p) {
     const int c = blockIdx.x;
     uint32_t* epoch = p.flag[p.rank] + P2P_EPOCH_OFF + c;
@@ -90,27 +92,27 @@ __global__ void __launch_bounds__(P2P_THREADS) allreduce_p2p_kernel(P2PParams p)
     const int64_t lo = slice * p.rank;
     const int64_t hi = min(lo + slice, p.n4);
     const int64_t stride = (int64_t)gridDim.x * P2P_THREADS;
-    for (int64_t j = lo + (int64_t)c * P2P_THREADS + threadIdx.x; j < hi; j += 2 * stride) {
-        const int64_t j1 = j + stride;
-        const bool two = j1 < hi;
-        float4 v0[W], v1[W];
+    for (int64_t j = lo + (int64_t)c * P2P_THREADS + threadIdx.x; j < hi; j += U * stride) {
+        float4 v[U][W];
 #pragma unroll
-        for (int q = 0; q < W; ++q) {
-            v0[q] = ld_volatile4(p.buf[q] + 4 * j);
-            if (two) v1[q] = ld_volatile4(p.buf[q] + 4 * j1);
+        for (int u = 0; u < U; ++u) {
+            const int64_t ju = j + u * stride;
+            if (ju < hi) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) v[u][q] = ld_volatile4(p.buf[q] + 4 * ju);
+            }
         }
-        float4 a = v0[0], b = two ? v1[0] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 1; q < W; ++q) {
-            a.x += v0[q].x; a.y += v0[q].y; a.z += v0[q].z; a.w += v0[q].w;
-            if (two) { b.x += v1[q].x; b.y += v1[q].y; b.z += v1[q].z; b.w += v1[q].w; }
-        }
-        a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale;
-        b.x *= p.scale; b.y *= p.scale; b.z *= p.scale; b.w *= p.scale;
+        for (int u = 0; u < U; ++u) {
+            const int64_t ju = j + u * stride;
+            if (ju < hi) {
+                float4 a = v[u][0];
 #pragma unroll
-        for (int q = 0; q < W; ++q) {
-            *reinterpret_cast<float4*>(p.buf[q] + 4 * j) = a;
-            if (two) *reinterpret_cast<float4*>(p.buf[q] + 4 * j1) = b;
+                for (int q = 1; q < W; ++q) { a.x += v[u][q].x; a.y += v[u][q].y; a.z += v[u][q].z; a.w += v[u][q].w; }
+                a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale;
+#pragma unroll
+                for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(p.buf[q] + 4 * ju) = a;
+            }
         }
     }
     p2p_barrier(p, c, e + 2);
@@ -173,7 +175,7 @@ extern "C" int mgnns_allreduce_p2p_f32(const uint64_t* bufs, const uint64_t* fla
     MG_REQUIRE(n >= 0 && (n & 3) == 0, "allreduce_p2p: n must be a multiple of 4 floats");
     MG_REQUIRE(bufs && flags, "allreduce_p2p: null pointer");
     if (n == 0) return 0;
-    if (ctas <= 0) ctas = 32;
+    if (ctas <= 0) ctas = 96;
     if (ctas > P2P_MAX_CTAS) ctas = P2P_MAX_CTAS;
     P2PParams p{};
     for (int q = 0; q < world; ++q) {
@@ -184,14 +186,14 @@ extern "C" int mgnns_allreduce_p2p_f32(const uint64_t* bufs, const uint64_t* fla
     p.rank = rank; p.world = world; p.n4 = n >> 2; p.scale = scale;
     cudaStream_t st = as_stream(stream);
     switch (world) {
-        case 1: allreduce_p2p_kernel<1><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 2: allreduce_p2p_kernel<2><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 3: allreduce_p2p_kernel<3><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 4: allreduce_p2p_kernel<4><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 5: allreduce_p2p_kernel<5><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 6: allreduce_p2p_kernel<6><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        case 7: allreduce_p2p_kernel<7><<<ctas, P2P_THREADS, 0, st>>>(p); break;
-        default: allreduce_p2p_kernel<8><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 1: allreduce_p2p_kernel<1, 4><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 2: allreduce_p2p_kernel<2, 8><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 3: allreduce_p2p_kernel<3, 5><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 4: allreduce_p2p_kernel<4, 4><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 5: allreduce_p2p_kernel<5, 3><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 6: allreduce_p2p_kernel<6, 3><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        case 7: allreduce_p2p_kernel<7, 2><<<ctas, P2P_THREADS, 0, st>>>(p); break;
+        default: allreduce_p2p_kernel<8, 2><<<ctas, P2P_THREADS, 0, st>>>(p); break;
     }
     MG_LAUNCH_CHECK("allreduce_p2p");
     return 0;

@@ -7,6 +7,7 @@ which, unlike a process-group collective, a multi-stream CUDA-graph capture reco
 (ref: the training step engine/Multi_GCN_Multihead_Att_engine.py:847-851).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -47,14 +48,15 @@ class PeerAllReduce:
     scale * (sum over ranks) on every rank, bit-identically, with one kernel on the current stream.  Every rank must
     call all_reduce_ the same number of times (the cross-GPU barriers count epochs on the device)."""
 
-    def __init__(self, numel, device, group=None, ctas=32):
+    def __init__(self, numel, device, group=None, ctas=None):
         if not dist.is_initialized():
             raise RuntimeError("PeerAllReduce needs an initialised torch.distributed process group (rendezvous only)")
         if numel % 4:
             raise ValueError("PeerAllReduce: numel must be a multiple of 4 floats")
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.numel, self.ctas = int(numel), int(ctas)
+        self.numel = int(numel)
+        self.ctas = int(ctas if ctas is not None else os.environ.get('MGNNS_P2P_CTAS', '96'))
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
             self._buf = _alloc(4 * max(self.numel, 4))
