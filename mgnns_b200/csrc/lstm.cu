@@ -250,15 +250,51 @@ __device__ __forceinline__ void cl_sync() {
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// Per-step exchange without a cluster barrier.  barrier.cluster.arrive.release makes every thread drain ALL its
+// outstanding stores first (ncu: 6 % of the forward kernel's and 18 % of the backward kernel's stall samples sat on
+// that fence, the per-step global result stores included) and a full cluster barrier costs ~380 cycles.  Instead the
+// remote stores are st.async ones that carry their own completion: each lands in the peer's shared memory and
+// decrements the transaction count of an mbarrier there, the consumer arms that mbarrier with the byte count it
+// expects per step and waits for its phase — one one-way trip (~215 cycles), no fence, and the global stores of the
+// step are never waited for.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra MB_WAIT_%=;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// value -> the peer CTA's shared memory at `remote_addr`, 4 bytes counted on the peer's mbarrier `remote_bar`
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mb_arrive_remote(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+
+// HT > 0: hidden size known at compile time (every shared-memory stride becomes an immediate offset: the runtime-H
+// version spent ~40 % of its issue slots on address arithmetic for the W / h loads); HT = 0: plan.H
+template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ G, const float* __restrict__ wt_f, const float* __restrict__ wt_r,
     float* __restrict__ Y, float* __restrict__ gates, float* __restrict__ csave, float* __restrict__ hprev) {
     extern __shared__ __align__(16) float sm[];
-    const int H = plan.H, Hh = H / 2, NC = 4 * Hh;          // NC = gate columns owned by this CTA
+    const int H = HT ? HT : plan.H, Hh = H / 2, NC = 4 * Hh;          // NC = gate columns owned by this CTA
     float* Wsm = sm;                                         // [H][NC]
     float* hs = Wsm + H * NC;                                // [2][H][TS]
     float* zp = hs + 2 * H * TS;                             // [2 k-halves][TS][NC]
     __shared__ int s_off[TS], s_len[TS];
+    __shared__ __align__(8) uint64_t full[2];                // full[b]: the peer's half of hs[b] has landed
     const int dir = blockIdx.y, tile = blockIdx.x >> 1;
     const uint32_t rank = cl_rank(), peer = rank ^ 1u;
     const float* __restrict__ WT = dir ? wt_r : wt_f;        // [H][4H]
@@ -267,6 +303,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         int s = plan.tiles[tile * TS + tid];
         s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
         s_len[tid] = s >= 0 ? plan.lens[s] : 0;
+    }
+    if (tid == 0) {
+        mb_init(&full[0], 1);
+        mb_init(&full[1], 1);
+        mb_fence_init();
     }
     for (int i = tid; i < H * NC; i += CL_THREADS) {
         const int k = i / NC, lc = i - k * NC, g = lc / Hh, uu = lc - g * Hh;
@@ -295,25 +336,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         p_s[q] = p_ok[q] ? p / Hh : 0;
         p_u[q] = p_ok[q] ? p % Hh : 0;
     }
-    int cur = 0;
-    for (int t = 0; t < tile_len; ++t) {
-        // prefetch this step's input projections while the recurrent product runs
-        float gin[2][4];
-        int64_t rowq[2];
-        bool act[2];
+    // input projections of one step for the thread's two (unit, sequence) pairs; the NEXT step's are fetched at the
+    // top of a step, so their L2 latency is off the per-step critical path
+    struct Gin { float g[4]; int64_t row; bool on; };
+    auto fetch = [&](int t, Gin (&gi)[2]) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+            gi[q].on = false;
+            gi[q].row = 0;
+            if (!p_ok[q] || t >= tile_len) continue;
             const int len = s_len[p_s[q]];
-            act[q] = p_ok[q] && t < len;
-            rowq[q] = 0;
-            if (act[q]) {
-                const int tt = dir ? (len - 1 - t) : t;
-                rowq[q] = s_off[p_s[q]] + tt;
-                const float* g_in = G + rowq[q] * (8 * H) + dir * 4 * H + rank * Hh + p_u[q];
+            if (t >= len) continue;
+            const int tt = dir ? (len - 1 - t) : t;
+            gi[q].row = s_off[p_s[q]] + tt;
+            const float* g_in = G + gi[q].row * (8 * H) + dir * 4 * H + rank * Hh + p_u[q];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) gin[q][g] = __ldg(g_in + g * H);
-            }
+            for (int g = 0; g < 4; ++g) gi[q].g[g] = __ldg(g_in + g * H);
+            gi[q].on = true;
         }
+    };
+    const uint32_t step_bytes = (uint32_t)(npairs * sizeof(float));     // what the peer sends per step
+    const uint32_t peer_full0 = cl_map(&full[0], peer), peer_full1 = cl_map(&full[1], peer);
+    Gin gin[2], gnx[2];
+    fetch(0, gin);
+    int cur = 0;
+    for (int t = 0; t < tile_len; ++t) {
+        fetch(t + 1, gnx);
+        if (tid == 0) mb_expect_tx(&full[cur ^ 1], step_bytes);
         if (zlive) {
             float a0[TS], a1[TS];
 #pragma unroll
@@ -335,6 +384,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         }
         __syncthreads();
         float* hnext = hs + (cur ^ 1) * H * TS;
+        const uint32_t peer_full = cur ? peer_full0 : peer_full1;          // the peer's full[cur ^ 1]
         float sv[2][7];                                      // i, f, g, o, c, h_prev, h of the two (unit, sequence) pairs
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -342,47 +392,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
             const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
             const float hold = hs[cur * H * TS + u * TS + s];
             float hnew = hold;
-            if (act[q]) {
+            if (gin[q].on) {
                 const float* z0 = zp + s * NC;
                 const float* z1 = zp + TS * NC + s * NC;
-                const float ig = sigmoidf_(z0[uu] + z1[uu] + gin[q][0]);
-                const float fg = sigmoidf_(z0[Hh + uu] + z1[Hh + uu] + gin[q][1]);
-                const float gg = tanhf_(z0[2 * Hh + uu] + z1[2 * Hh + uu] + gin[q][2]);
-                const float og = sigmoidf_(z0[3 * Hh + uu] + z1[3 * Hh + uu] + gin[q][3]);
+                const float ig = sigmoidf_(z0[uu] + z1[uu] + gin[q].g[0]);
+                const float fg = sigmoidf_(z0[Hh + uu] + z1[Hh + uu] + gin[q].g[1]);
+                const float gg = tanhf_(z0[2 * Hh + uu] + z1[2 * Hh + uu] + gin[q].g[2]);
+                const float og = sigmoidf_(z0[3 * Hh + uu] + z1[3 * Hh + uu] + gin[q].g[3]);
                 cst[q] = fg * cst[q] + ig * gg;
                 hnew = og * tanhf_(cst[q]);
                 sv[q][0] = ig; sv[q][1] = fg; sv[q][2] = gg; sv[q][3] = og; sv[q][4] = cst[q]; sv[q][5] = hold; sv[q][6] = hnew;
             }
             hnext[u * TS + s] = hnew;
-            cl_store(cl_map(hnext + u * TS + s, peer), hnew);
+            st_async_f32(cl_map(hnext + u * TS + s, peer), hnew, peer_full);
         }
-        cl_arrive();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            if (!act[q]) continue;
+            if (!gin[q].on) continue;
             const int u = rank * Hh + p_u[q];
-            const int64_t row = rowq[q];
+            const int64_t row = gin[q].row;
             Y[row * (2 * H) + dir * H + u] = sv[q][6];
             float* gs = gates + (row * 2 + dir) * (4 * H);
             gs[u] = sv[q][0]; gs[H + u] = sv[q][1]; gs[2 * H + u] = sv[q][2]; gs[3 * H + u] = sv[q][3];
             csave[(row * 2 + dir) * H + u] = sv[q][4];
             hprev[(row * 2 + dir) * H + u] = sv[q][5];
         }
-        cl_wait();
+        // hs[cur ^ 1] complete: own half (barrier below), the peer's half (its st.async bytes counted on full[cur ^ 1]).
+        // The peer overwrites hs[cur] only in ITS step t + 1, i.e. after it has received every byte of this step from
+        // here — which every thread sends after its last read of hs[cur].
+        __syncthreads();
+        mb_wait(&full[cur ^ 1], (uint32_t)(t >> 1) & 1u);
         cur ^= 1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) gin[q] = gnx[q];
     }
+    cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
 }
 
+template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_bwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ dY, const float* __restrict__ gates, const float* __restrict__ csave,
     const float* __restrict__ whh_f, const float* __restrict__ whh_r, float* __restrict__ dG) {
     extern __shared__ __align__(16) float sm[];
-    const int H = plan.H, Hh = H / 2;
+    const int H = HT ? HT : plan.H, Hh = H / 2;
     float* Wb = sm;                                          // [4H][Hh]: W_hh columns of this CTA's hidden units
     float* dzs = Wb + 4 * H * Hh;                            // [4H][TS]
     float* part = dzs + 4 * H * TS;                          // [4][TS][Hh]
     float* dh = part + 4 * TS * Hh;                          // [TS][Hh]
     __shared__ int s_off[TS], s_len[TS];
+    __shared__ __align__(8) uint64_t full, freeb;            // full: the peer's gate gradients of this step have landed;
+                                                             // freeb: the peer has finished reading what was sent to it
     const int dir = blockIdx.y, tile = blockIdx.x >> 1;
     const uint32_t rank = cl_rank(), peer = rank ^ 1u;
     const float* __restrict__ W = dir ? whh_r : whh_f;       // [4H][H]
@@ -391,6 +450,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         int s = plan.tiles[tile * TS + tid];
         s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
         s_len[tid] = s >= 0 ? plan.lens[s] : 0;
+    }
+    if (tid == 0) {
+        mb_init(&full, 1);
+        mb_init(&freeb, 1);
+        mb_fence_init();
     }
     for (int i = tid; i < 4 * H * Hh; i += CL_THREADS) {
         const int j = i / Hh, kk = i - j * Hh;
@@ -443,9 +507,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
             sv[q].on = true;
         }
     };
+    const uint32_t step_bytes = (uint32_t)(4 * npairs * sizeof(float));  // what the peer sends per step
+    const uint32_t peer_full = cl_map(&full, peer), peer_free = cl_map(&freeb, peer);
     Saved cur_sv[2], nxt_sv[2];
     fetch(tile_len - 1, cur_sv);
     for (int t = tile_len - 1; t >= 0; --t) {
+        const int it = tile_len - 1 - t;                     // 0-based step count
+        if (tid == 0) mb_expect_tx(&full, step_bytes);
         // ---- phase 1: gate gradients for this CTA's hidden units -------------------------------------
         float dzq[2][4];
 #pragma unroll
@@ -466,14 +534,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 dz[3] = dhv * tc * og * (1.f - og);
                 dcs[q] = dct * fg;
             }
+            // the peer's dzs may be overwritten once it has finished phase 2 of the previous step
+            if (it > 0) mb_wait(&freeb, (uint32_t)(it - 1) & 1u);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float* slot = dzs + (g * H + u) * TS + s;
                 *slot = dz[g];
-                cl_store(cl_map(slot, peer), dz[g]);
+                st_async_f32(cl_map(slot, peer), dz[g], peer_full);
             }
         }
-        cl_arrive();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (!p_ok[q] || !cur_sv[q].on) continue;
@@ -482,7 +551,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
             out[u] = dzq[q][0]; out[H + u] = dzq[q][1]; out[2 * H + u] = dzq[q][2]; out[3 * H + u] = dzq[q][3];
         }
         fetch(t - 1, nxt_sv);
-        cl_wait();
+        __syncthreads();                                     // own half of dzs
+        mb_wait(&full, (uint32_t)it & 1u);                   // the peer's half
         // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
         if (t > 0) {
             float acc[TS];
@@ -503,14 +573,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
 #pragma unroll
                 for (int s = 0; s < TS; ++s) part[(jq * TS + s) * Hh + kk2] = acc[s];
             }
-            __syncthreads();
+            __syncthreads();                                 // every thread has finished reading dzs
+            if (tid == 0) mb_arrive_remote(peer_free);       // ... so the peer may send its next step's gradients
             for (int i = tid; i < TS * Hh; i += CL_THREADS)
                 dh[i] = part[i] + part[TS * Hh + i] + part[2 * TS * Hh + i] + part[3 * TS * Hh + i];
+            __syncthreads();                                 // dh complete before phase 1 of the next step reads it
         }
-        cl_sync();      // dzs may be overwritten (also remotely) by the next step only after both CTAs finished phase 2
 #pragma unroll
         for (int q = 0; q < 2; ++q) cur_sv[q] = nxt_sv[q];
     }
+    cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
 }
 
 static size_t lstm_cl_fwd_smem(int H) { return sizeof(float) * ((size_t)H * 2 * H + 2 * H * TS + 2 * TS * 2 * H); }
@@ -542,11 +614,15 @@ extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, c
         // cluster-of-2 variant with W_hh resident in (distributed) shared memory
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(lstm_rec_fwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(lstm_rec_fwd_cl_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_rec_fwd_cl_kernel<150>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
             MG_REQUIRE(e == cudaSuccess, "lstm_rec_fwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
             configured = true;
         }
-        lstm_rec_fwd_cl_kernel<<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+        if (H == 150)      // the reference's hidden size (entry: --hidden_size 150)
+            lstm_rec_fwd_cl_kernel<150><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+        else
+            lstm_rec_fwd_cl_kernel<0><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
         MG_LAUNCH_CHECK("lstm_rec_fwd_cl");
         return 0;
     }
@@ -566,11 +642,15 @@ extern "C" int mgnns_lstm_rec_bwd(const int32_t* offsets, const int32_t* lens, c
     if (smem <= 225 * 1024 && H <= 2 * 80) {
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(lstm_rec_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(lstm_rec_bwd_cl_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_rec_bwd_cl_kernel<150>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
             MG_REQUIRE(e == cudaSuccess, "lstm_rec_bwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
             configured = true;
         }
-        lstm_rec_bwd_cl_kernel<<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+        if (H == 150)
+            lstm_rec_bwd_cl_kernel<150><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+        else
+            lstm_rec_bwd_cl_kernel<0><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
         MG_LAUNCH_CHECK("lstm_rec_bwd_cl");
         return 0;
     }

@@ -41,4 +41,16 @@ if which in ('spmm', 'gcn', 'all'):
         for _ in range(3):
             y = gc(x, csr, ops.ACT_RELU) if which != 'spmm' else csr.spmm(x)
     torch.cuda.synchronize()
+if which in ('lstm', 'all'):
+    sys.path.insert(0, ROOT)
+    import bench
+    lstm = torch.nn.LSTM(300, 150, num_layers=2, batch_first=True, bidirectional=True).to(dev)
+    hb = bench.host_batch(B, 0)
+    lens = hb['lens']
+    plan = ops.LstmPlan(lens, 100, dev, None)
+    x = torch.randn(plan.capacity, 300, device=dev, requires_grad=True)
+    for _ in range(3):
+        y = ops.packed_bilstm(lstm, x, plan, False)
+        y.sum().backward()
+    torch.cuda.synchronize()
 print('done', which)

@@ -72,8 +72,9 @@ for k, v in sorted(total.items(), key=lambda kv: -alone.get(kv[0], 0))[:28]:
 
 # compact Gantt of the long activities (>= 40 us) and of every stream's busy span
 print("\nstart_ms  end_ms  stream  kernel")
+min_dur = 0 if os.environ.get('MGNNS_TIMELINE_ALL') == '1' else 40
 for e in step:
-    if e['dur'] >= 40:
+    if e['dur'] >= min_dur:
         print("%7.3f %7.3f  %6s  %s" % ((e['ts'] - t0) / 1e3, (e['ts'] + e['dur'] - t0) / 1e3, e['args'].get('stream'), e['name'][:70]))
 by_stream = defaultdict(list)
 for e in step:
