@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_rec_bwd_kernel(
 // CTAs exchange only the new hidden state (forward) / gate gradients (backward) through DSMEM stores
 // followed by one cluster barrier.
 // =====================================================================================================
-constexpr int CL_THREADS = 320;
+constexpr int CL_THREADS = 640;
 
 __device__ __forceinline__ uint32_t cl_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cl_map(const void* p, uint32_t rank) {
@@ -278,12 +278,28 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
 }
+// 16 bytes at once: the exchanged blocks are contiguous in shared memory, so a warp's stores form one 512-byte run
+// (32 scattered 4-byte DSMEM stores per warp — the layout's natural (unit, sequence) -> address map has a 32-byte
+// stride — cost a remote transaction each)
+__device__ __forceinline__ void st_async_f32x4(uint32_t remote_addr, const float4& v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ void mb_arrive_remote(uint32_t remote_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 
 // HT > 0: hidden size known at compile time (every shared-memory stride becomes an immediate offset: the runtime-H
 // version spent ~40 % of its issue slots on address arithmetic for the W / h loads); HT = 0: plan.H
+//
+// 640 threads (20 warps, five per scheduler).  The per-step product is bound by instruction issue (16 FMA + 4 LDS per
+// thread and k), and with 320 threads — 2.5 warps per scheduler — the FMA pipe sat at 31 % (ncu): the loads of one
+// warp were not covered by the FMAs of another.  So the K range is cut into FOUR groups of 160 threads (two columns x
+// eight sequences per thread, as before), the four partial sums meet in shared memory, and the gate phase has one
+// (unit, sequence) pair per thread instead of two in sequence.
+constexpr int CL_KGROUPS = 4;
+
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ G, const float* __restrict__ wt_f, const float* __restrict__ wt_r,
@@ -292,7 +308,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     const int H = HT ? HT : plan.H, Hh = H / 2, NC = 4 * Hh;          // NC = gate columns owned by this CTA
     float* Wsm = sm;                                         // [H][NC]
     float* hs = Wsm + H * NC;                                // [2][H][TS]
-    float* zp = hs + 2 * H * TS;                             // [2 k-halves][TS][NC]
+    float* zp = hs + 2 * H * TS;                             // [CL_KGROUPS][TS][NC]
     __shared__ int s_off[TS], s_len[TS];
     __shared__ __align__(8) uint64_t full[2];                // full[b]: the peer's half of hs[b] has landed
     const int dir = blockIdx.y, tile = blockIdx.x >> 1;
@@ -318,46 +334,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     int tile_len = 0;
 #pragma unroll
     for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
-    cl_sync();                                               // peer's buffers are initialised before any remote store
+    cl_sync();                                               // peer's buffers / mbarriers are initialised before any remote store
 
-    // z-phase mapping: two groups of 160 threads split the k range; each thread owns two columns
+    // z-phase mapping: four groups of 160 threads split the k range; each thread owns two columns
     const int grp = tid / 160, jl = tid % 160;
     const bool zlive = jl < NC / 2;
-    const int k_lo = grp ? H / 2 : 0, k_hi = grp ? H : H / 2;
-    // activation mapping: pairs (unit, sequence); at most two per thread, fixed for the whole kernel
+    const int k_lo = (H * grp) / CL_KGROUPS, k_hi = (H * (grp + 1)) / CL_KGROUPS;
+    // gate mapping: one (unit, sequence) pair per thread, fixed for the whole kernel (Hh * TS <= 640 pairs)
     const int npairs = Hh * TS;
-    int p_s[2], p_u[2];
-    bool p_ok[2];
-    float cst[2] = {0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int p = tid + q * CL_THREADS;
-        p_ok[q] = p < npairs;
-        p_s[q] = p_ok[q] ? p / Hh : 0;
-        p_u[q] = p_ok[q] ? p % Hh : 0;
-    }
-    // input projections of one step for the thread's two (unit, sequence) pairs; the NEXT step's are fetched at the
-    // top of a step, so their L2 latency is off the per-step critical path
+    const bool p_ok = tid < npairs;
+    const int p_s = p_ok ? tid / Hh : 0, p_u = p_ok ? tid % Hh : 0;
+    const int p_len = s_len[p_s], p_off = s_off[p_s];
+    float cst = 0.f;
+    // input projections of one step for the thread's pair; the NEXT step's are fetched at the top of a step, so their
+    // L2 latency is off the per-step critical path
     struct Gin { float g[4]; int64_t row; bool on; };
-    auto fetch = [&](int t, Gin (&gi)[2]) {
+    auto fetch = [&](int t, Gin& gi) {
+        gi.on = false;
+        gi.row = 0;
+        if (!p_ok || t >= p_len) return;
+        const int tt = dir ? (p_len - 1 - t) : t;
+        gi.row = p_off + tt;
+        const float* g_in = G + gi.row * (8 * H) + dir * 4 * H + rank * Hh + p_u;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            gi[q].on = false;
-            gi[q].row = 0;
-            if (!p_ok[q] || t >= tile_len) continue;
-            const int len = s_len[p_s[q]];
-            if (t >= len) continue;
-            const int tt = dir ? (len - 1 - t) : t;
-            gi[q].row = s_off[p_s[q]] + tt;
-            const float* g_in = G + gi[q].row * (8 * H) + dir * 4 * H + rank * Hh + p_u[q];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) gi[q].g[g] = __ldg(g_in + g * H);
-            gi[q].on = true;
-        }
+        for (int g = 0; g < 4; ++g) gi.g[g] = __ldg(g_in + g * H);
+        gi.on = true;
     };
     const uint32_t step_bytes = (uint32_t)(npairs * sizeof(float));     // what the peer sends per step
     const uint32_t peer_full0 = cl_map(&full[0], peer), peer_full1 = cl_map(&full[1], peer);
-    Gin gin[2], gnx[2];
+    const int u_glob = rank * Hh + p_u;
+    Gin gin, gnx;
     fetch(0, gin);
     int cur = 0;
     for (int t = 0; t < tile_len; ++t) {
@@ -368,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
 #pragma unroll
             for (int s = 0; s < TS; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
             const float* hcur = hs + cur * H * TS;
-#pragma unroll 5
+#pragma unroll 4
             for (int k = k_lo; k < k_hi; ++k) {
                 const float w0 = Wsm[k * NC + jl], w1 = Wsm[k * NC + NC / 2 + jl];
                 const float4 h0 = *reinterpret_cast<const float4*>(hcur + k * TS);
@@ -385,49 +391,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         __syncthreads();
         float* hnext = hs + (cur ^ 1) * H * TS;
         const uint32_t peer_full = cur ? peer_full0 : peer_full1;          // the peer's full[cur ^ 1]
-        float sv[2][7];                                      // i, f, g, o, c, h_prev, h of the two (unit, sequence) pairs
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (!p_ok[q]) continue;
-            const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
-            const float hold = hs[cur * H * TS + u * TS + s];
+        float sv[7];                                         // i, f, g, o, c, h_prev, h of the thread's pair
+        if (p_ok) {
+            const float hold = hs[cur * H * TS + u_glob * TS + p_s];
             float hnew = hold;
-            if (gin[q].on) {
-                const float* z0 = zp + s * NC;
-                const float* z1 = zp + TS * NC + s * NC;
-                const float ig = sigmoidf_(z0[uu] + z1[uu] + gin[q].g[0]);
-                const float fg = sigmoidf_(z0[Hh + uu] + z1[Hh + uu] + gin[q].g[1]);
-                const float gg = tanhf_(z0[2 * Hh + uu] + z1[2 * Hh + uu] + gin[q].g[2]);
-                const float og = sigmoidf_(z0[3 * Hh + uu] + z1[3 * Hh + uu] + gin[q].g[3]);
-                cst[q] = fg * cst[q] + ig * gg;
-                hnew = og * tanhf_(cst[q]);
-                sv[q][0] = ig; sv[q][1] = fg; sv[q][2] = gg; sv[q][3] = og; sv[q][4] = cst[q]; sv[q][5] = hold; sv[q][6] = hnew;
-            }
-            hnext[u * TS + s] = hnew;
-            st_async_f32(cl_map(hnext + u * TS + s, peer), hnew, peer_full);
-        }
+            if (gin.on) {
+                float zg[4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (!gin[q].on) continue;
-            const int u = rank * Hh + p_u[q];
-            const int64_t row = gin[q].row;
-            Y[row * (2 * H) + dir * H + u] = sv[q][6];
-            float* gs = gates + (row * 2 + dir) * (4 * H);
-            gs[u] = sv[q][0]; gs[H + u] = sv[q][1]; gs[2 * H + u] = sv[q][2]; gs[3 * H + u] = sv[q][3];
-            csave[(row * 2 + dir) * H + u] = sv[q][4];
-            hprev[(row * 2 + dir) * H + u] = sv[q][5];
+                for (int g = 0; g < 4; ++g) {
+                    float acc = gin.g[g];
+#pragma unroll
+                    for (int kg = 0; kg < CL_KGROUPS; ++kg) acc += zp[(kg * TS + p_s) * NC + g * Hh + p_u];
+                    zg[g] = acc;
+                }
+                const float ig = sigmoidf_(zg[0]), fg = sigmoidf_(zg[1]), gg = tanhf_(zg[2]), og = sigmoidf_(zg[3]);
+                cst = fg * cst + ig * gg;
+                hnew = og * tanhf_(cst);
+                sv[0] = ig; sv[1] = fg; sv[2] = gg; sv[3] = og; sv[4] = cst; sv[5] = hold; sv[6] = hnew;
+            }
+            hnext[u_glob * TS + p_s] = hnew;
+            if (gin.on) {
+                const int64_t row = gin.row;
+                Y[row * (2 * H) + dir * H + u_glob] = sv[6];
+                float* gs = gates + (row * 2 + dir) * (4 * H);
+                gs[u_glob] = sv[0]; gs[H + u_glob] = sv[1]; gs[2 * H + u_glob] = sv[2]; gs[3 * H + u_glob] = sv[3];
+                csave[(row * 2 + dir) * H + u_glob] = sv[4];
+                hprev[(row * 2 + dir) * H + u_glob] = sv[5];
+            }
         }
-        // hs[cur ^ 1] complete: own half (barrier below), the peer's half (its st.async bytes counted on full[cur ^ 1]).
-        // The peer overwrites hs[cur] only in ITS step t + 1, i.e. after it has received every byte of this step from
-        // here — which every thread sends after its last read of hs[cur].
+        // hs[cur ^ 1] complete: own half (barrier below; it is one contiguous block of Hh * TS floats, which the first
+        // Hh * TS / 4 threads then copy to the peer 16 bytes each), the peer's half (its bytes counted on
+        // full[cur ^ 1]).  The peer overwrites hs[cur] only in ITS step t + 1, i.e. after it has received every byte of
+        // this step from here — which is sent after every thread's last read of hs[cur].
         __syncthreads();
+        if (tid < npairs / 4) {
+            const float* src = hnext + rank * Hh * TS + 4 * tid;
+            st_async_f32x4(cl_map(src, peer), *reinterpret_cast<const float4*>(src), peer_full);
+        }
         mb_wait(&full[cur ^ 1], (uint32_t)(t >> 1) & 1u);
         cur ^= 1;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) gin[q] = gnx[q];
+        gin = gnx;
     }
     cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
 }
+
+constexpr int CL_JGROUPS = 8;        // backward phase 2: the 4H gate rows are cut into eight groups of H/2
 
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_bwd_cl_kernel(
@@ -437,8 +445,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     const int H = HT ? HT : plan.H, Hh = H / 2;
     float* Wb = sm;                                          // [4H][Hh]: W_hh columns of this CTA's hidden units
     float* dzs = Wb + 4 * H * Hh;                            // [4H][TS]
-    float* part = dzs + 4 * H * TS;                          // [4][TS][Hh]
-    float* dh = part + 4 * TS * Hh;                          // [TS][Hh]
+    float* part = dzs + 4 * H * TS;                          // [CL_JGROUPS][TS][Hh]
+    float* dh = part + CL_JGROUPS * TS * Hh;                 // [TS][Hh]
     __shared__ int s_off[TS], s_len[TS];
     __shared__ __align__(8) uint64_t full, freeb;            // full: the peer's gate gradients of this step have landed;
                                                              // freeb: the peer has finished reading what was sent to it
@@ -467,91 +475,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
     cl_sync();
 
+    // phase-1 mapping: one (unit, sequence) pair per thread
     const int npairs = Hh * TS;
-    int p_s[2], p_u[2];
-    bool p_ok[2];
-    float dcs[2] = {0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int p = tid + q * CL_THREADS;
-        p_ok[q] = p < npairs;
-        p_s[q] = p_ok[q] ? p / Hh : 0;
-        p_u[q] = p_ok[q] ? p % Hh : 0;
-    }
-    // phase-2 mapping: thread (kk, quarter of the 4H gate rows)
+    const bool p_ok = tid < npairs;
+    const int p_s = p_ok ? tid / Hh : 0, p_u = p_ok ? tid % Hh : 0;
+    const int p_len = s_len[p_s], p_off = s_off[p_s];
+    const int u_glob = rank * Hh + p_u;
+    float dcs = 0.f;
+    // phase-2 mapping: thread (kk, one of eight groups of gate rows)
     const int kk2 = tid % 80, jq = tid / 80;
     const bool live2 = kk2 < Hh;
-    // saved forward tensors of one time step for the thread's two (unit, sequence) pairs; the NEXT step's are fetched
-    // while this step's barrier and product run, so their L2 latency is off the per-step critical path
+    // saved forward tensors of one time step for the thread's pair; the NEXT step's are fetched while this step's
+    // exchange and product run, so their L2 latency is off the per-step critical path
     struct Saved { float ig, fg, gg, og, c, cprev, dy; int64_t row; bool on; };
-    auto fetch = [&](int t, Saved (&sv)[2]) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            sv[q].on = false;
-            if (!p_ok[q] || t < 0) continue;
-            const int s = p_s[q], u = rank * Hh + p_u[q];
-            const int len = s_len[s];
-            if (t >= len) continue;
-            const int tt = dir ? (len - 1 - t) : t;
-            const int64_t row = s_off[s] + tt;
-            const float* gs = gates + (row * 2 + dir) * (4 * H);
-            sv[q].ig = __ldg(gs + u); sv[q].fg = __ldg(gs + H + u); sv[q].gg = __ldg(gs + 2 * H + u); sv[q].og = __ldg(gs + 3 * H + u);
-            sv[q].c = __ldg(csave + (row * 2 + dir) * H + u);
-            sv[q].cprev = 0.f;
-            if (t > 0) {
-                const int64_t rp = dir ? row + 1 : row - 1;
-                sv[q].cprev = __ldg(csave + (rp * 2 + dir) * H + u);
-            }
-            sv[q].dy = __ldg(dY + row * (2 * H) + dir * H + u);
-            sv[q].row = row;
-            sv[q].on = true;
+    auto fetch = [&](int t, Saved& sv) {
+        sv.on = false;
+        if (!p_ok || t < 0 || t >= p_len) return;
+        const int tt = dir ? (p_len - 1 - t) : t;
+        const int64_t row = p_off + tt;
+        const float* gs = gates + (row * 2 + dir) * (4 * H);
+        sv.ig = __ldg(gs + u_glob); sv.fg = __ldg(gs + H + u_glob); sv.gg = __ldg(gs + 2 * H + u_glob); sv.og = __ldg(gs + 3 * H + u_glob);
+        sv.c = __ldg(csave + (row * 2 + dir) * H + u_glob);
+        sv.cprev = 0.f;
+        if (t > 0) {
+            const int64_t rp = dir ? row + 1 : row - 1;
+            sv.cprev = __ldg(csave + (rp * 2 + dir) * H + u_glob);
         }
+        sv.dy = __ldg(dY + row * (2 * H) + dir * H + u_glob);
+        sv.row = row;
+        sv.on = true;
     };
     const uint32_t step_bytes = (uint32_t)(4 * npairs * sizeof(float));  // what the peer sends per step
     const uint32_t peer_full = cl_map(&full, peer), peer_free = cl_map(&freeb, peer);
-    Saved cur_sv[2], nxt_sv[2];
+    Saved cur_sv, nxt_sv;
     fetch(tile_len - 1, cur_sv);
     for (int t = tile_len - 1; t >= 0; --t) {
         const int it = tile_len - 1 - t;                     // 0-based step count
         if (tid == 0) mb_expect_tx(&full, step_bytes);
         // ---- phase 1: gate gradients for this CTA's hidden units -------------------------------------
-        float dzq[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (!p_ok[q]) continue;
-            const int s = p_s[q], uu = p_u[q], u = rank * Hh + uu;
-            float (&dz)[4] = dzq[q];
-            dz[0] = dz[1] = dz[2] = dz[3] = 0.f;
-            if (cur_sv[q].on) {
-                const float ig = cur_sv[q].ig, fg = cur_sv[q].fg, gg = cur_sv[q].gg, og = cur_sv[q].og;
-                const float c = cur_sv[q].c, cprev = cur_sv[q].cprev;
-                const float dhv = cur_sv[q].dy + dh[s * Hh + uu];
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p_ok) {
+            if (cur_sv.on) {
+                const float ig = cur_sv.ig, fg = cur_sv.fg, gg = cur_sv.gg, og = cur_sv.og;
+                const float c = cur_sv.c, cprev = cur_sv.cprev;
+                const float dhv = cur_sv.dy + dh[p_s * Hh + p_u];
                 const float tc = tanhf_(c);
-                const float dct = dcs[q] + dhv * og * (1.f - tc * tc);
+                const float dct = dcs + dhv * og * (1.f - tc * tc);
                 dz[0] = dct * gg * ig * (1.f - ig);
                 dz[1] = dct * cprev * fg * (1.f - fg);
                 dz[2] = dct * ig * (1.f - gg * gg);
                 dz[3] = dhv * tc * og * (1.f - og);
-                dcs[q] = dct * fg;
+                dcs = dct * fg;
             }
-            // the peer's dzs may be overwritten once it has finished phase 2 of the previous step
-            if (it > 0) mb_wait(&freeb, (uint32_t)(it - 1) & 1u);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float* slot = dzs + (g * H + u) * TS + s;
-                *slot = dz[g];
-                st_async_f32(cl_map(slot, peer), dz[g], peer_full);
+            for (int g = 0; g < 4; ++g) dzs[(g * H + u_glob) * TS + p_s] = dz[g];
+            if (cur_sv.on) {
+                float* out = dG + cur_sv.row * (8 * H) + dir * 4 * H;
+                out[u_glob] = dz[0]; out[H + u_glob] = dz[1]; out[2 * H + u_glob] = dz[2]; out[3 * H + u_glob] = dz[3];
             }
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (!p_ok[q] || !cur_sv[q].on) continue;
-            const int u = rank * Hh + p_u[q];
-            float* out = dG + cur_sv[q].row * (8 * H) + dir * 4 * H;
-            out[u] = dzq[q][0]; out[H + u] = dzq[q][1]; out[2 * H + u] = dzq[q][2]; out[3 * H + u] = dzq[q][3];
         }
         fetch(t - 1, nxt_sv);
-        __syncthreads();                                     // own half of dzs
+        __syncthreads();                                     // own half of dzs: four contiguous blocks of Hh * TS floats
+        if (p_ok) {
+            // the peer's dzs may be overwritten once it has finished phase 2 of the previous step
+            if (it > 0) mb_wait(&freeb, (uint32_t)(it - 1) & 1u);
+            const int g = tid / (npairs / 4), r = tid - g * (npairs / 4);
+            const float* src = dzs + (g * H + rank * Hh) * TS + 4 * r;
+            st_async_f32x4(cl_map(src, peer), *reinterpret_cast<const float4*>(src), peer_full);
+        }
         mb_wait(&full, (uint32_t)it & 1u);                   // the peer's half
         // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
         if (t > 0) {
@@ -559,9 +550,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
 #pragma unroll
             for (int s = 0; s < TS; ++s) acc[s] = 0.f;
             if (live2) {
-                const int j0 = jq * H;
+                const int j0 = jq * Hh;                      // 4H / 8 gate rows per group
 #pragma unroll 5
-                for (int j = 0; j < H; ++j) {
+                for (int j = 0; j < Hh; ++j) {
                     const float w = Wb[(j0 + j) * Hh + kk2];
                     const float4 d0 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS);
                     const float4 d1 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS + 4);
@@ -575,18 +566,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
             }
             __syncthreads();                                 // every thread has finished reading dzs
             if (tid == 0) mb_arrive_remote(peer_free);       // ... so the peer may send its next step's gradients
-            for (int i = tid; i < TS * Hh; i += CL_THREADS)
-                dh[i] = part[i] + part[TS * Hh + i] + part[2 * TS * Hh + i] + part[3 * TS * Hh + i];
+            if (tid < TS * Hh) {
+                float v = 0.f;
+#pragma unroll
+                for (int g = 0; g < CL_JGROUPS; ++g) v += part[g * TS * Hh + tid];
+                dh[tid] = v;
+            }
             __syncthreads();                                 // dh complete before phase 1 of the next step reads it
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) cur_sv[q] = nxt_sv[q];
+        cur_sv = nxt_sv;
     }
     cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
 }
 
-static size_t lstm_cl_fwd_smem(int H) { return sizeof(float) * ((size_t)H * 2 * H + 2 * H * TS + 2 * TS * 2 * H); }
-static size_t lstm_cl_bwd_smem(int H) { return sizeof(float) * ((size_t)4 * H * (H / 2) + 4 * H * TS + 4 * TS * (H / 2) + TS * (H / 2)); }
+static size_t lstm_cl_fwd_smem(int H) { return sizeof(float) * ((size_t)H * 2 * H + 2 * H * TS + (size_t)CL_KGROUPS * TS * 2 * H); }
+static size_t lstm_cl_bwd_smem(int H) { return sizeof(float) * ((size_t)4 * H * (H / 2) + 4 * H * TS + (size_t)CL_JGROUPS * TS * (H / 2) + TS * (H / 2)); }
 
 }  // namespace mgnns
 
