@@ -88,4 +88,22 @@ __device__ __forceinline__ void stg4_l2(float* ptr, const float4& v, uint64_t po
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Packed fp32 FMA (sm_100: SASS FFMA2, two independent round-to-nearest fp32 FMAs per lane and instruction — the
+// same bits as two scalar FFMAs).  The FP32 pipe is no faster, but an issue-bound inner product (LSTM recurrence,
+// CUDA-core GEMM) spends half the issue slots on its FMAs; pack_f32x2(w, w) folds into FFMA2's scalar-broadcast
+// operand form, so a scalar x pair product costs no extra move.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 }  // namespace mgnns

@@ -104,11 +104,13 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
     const int ktiles = (kend - kbase + BK - 1) / BK;
     const int total = ktiles * p.reduce;
 
-    float acc[4 * RM][4 * RN];
+    // accumulators in pairs along n: one FFMA2 (two exact fp32 FMAs, scalar a x pair of b) per pair and k — the
+    // product loop is issue bound, and this halves its FMA instructions (same bits as scalar FFMA)
+    unsigned long long acc2[4 * RM][2 * RN];
 #pragma unroll
     for (int i = 0; i < 4 * RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4 * RN; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 2 * RN; ++j) acc2[i][j] = 0ull;
 
     float4 ra[NLA], rb[NLB];
     auto fetch = [&](int t) {
@@ -130,7 +132,8 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
         if (t + 1 < total) fetch(t + 1);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            float a[4 * RM], b[4 * RN];
+            float a[4 * RM];
+            unsigned long long b2[2 * RN];
 #pragma unroll
             for (int g = 0; g < RM; ++g) {
                 float4 v = *reinterpret_cast<const float4*>(&As[cur][k][g * 64 + ty * 4]);
@@ -138,13 +141,15 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
             }
 #pragma unroll
             for (int g = 0; g < RN; ++g) {
-                float4 v = *reinterpret_cast<const float4*>(&Bs[cur][k][g * 64 + tx * 4]);
-                b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&Bs[cur][k][g * 64 + tx * 4]);
+                b2[g * 2 + 0] = v.x; b2[g * 2 + 1] = v.y;
             }
 #pragma unroll
-            for (int i = 0; i < 4 * RM; ++i)
+            for (int i = 0; i < 4 * RM; ++i) {
+                const unsigned long long aa = pack_f32x2(a[i], a[i]);
 #pragma unroll
-                for (int j = 0; j < 4 * RN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 2 * RN; ++j) acc2[i][j] = fma_f32x2(aa, b2[j], acc2[i][j]);
+            }
         }
         if (t + 1 < total) {
             store_tile<BM, TA, NLA>(ra, As[cur ^ 1], tid);
@@ -152,6 +157,12 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(GemmParams p) {
         }
         __syncthreads();
     }
+
+    float acc[4 * RM][4 * RN];
+#pragma unroll
+    for (int i = 0; i < 4 * RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * RN; ++j) unpack_f32x2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 
     const bool to_ws = p.ksplit > 1 && p.ws != nullptr;
     float* Cz = to_ws ? p.ws + (int64_t)z * p.M * p.N : p.C + (int64_t)zpair * p.strideC;

@@ -265,11 +265,15 @@ __device__ __forceinline__ void mb_fence_init() { asm volatile("fence.mbarrier_i
 __device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Default semantics (acquire at CTA scope), as for any transaction barrier fed by another CTA of the cluster (TMA
+// multicast, st.async): the data lands in THIS CTA's shared memory and complete_tx orders it before the phase flip.
+// The .acquire.cluster form makes ptxas emit CCTL.IVALL — an L1 invalidate that first waits for every outstanding
+// global load, i.e. for the next step's prefetch: ncu showed 5 % of all stall samples on that one instruction.
 __device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "MB_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra MB_WAIT_%=;\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
@@ -339,7 +343,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     // z-phase mapping: four groups of 160 threads split the k range; each thread owns two columns
     const int grp = tid / 160, jl = tid % 160;
     const bool zlive = jl < NC / 2;
-    const int k_lo = (H * grp) / CL_KGROUPS, k_hi = (H * (grp + 1)) / CL_KGROUPS;
     // gate mapping: one (unit, sequence) pair per thread, fixed for the whole kernel (Hh * TS <= 640 pairs)
     const int npairs = Hh * TS;
     const bool p_ok = tid < npairs;
@@ -367,27 +370,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     fetch(0, gin);
     int cur = 0;
     for (int t = 0; t < tile_len; ++t) {
-        fetch(t + 1, gnx);
         if (tid == 0) mb_expect_tx(&full[cur ^ 1], step_bytes);
         if (zlive) {
-            float a0[TS], a1[TS];
+            // two columns x eight sequences per thread; sequences in pairs, one FFMA2 per (column, pair) and k
+            unsigned long long a0[TS / 2], a1[TS / 2];
 #pragma unroll
-            for (int s = 0; s < TS; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+            for (int s = 0; s < TS / 2; ++s) { a0[s] = 0ull; a1[s] = 0ull; }
             const float* hcur = hs + cur * H * TS;
-#pragma unroll 4
-            for (int k = k_lo; k < k_hi; ++k) {
+            auto body = [&](int k) {
                 const float w0 = Wsm[k * NC + jl], w1 = Wsm[k * NC + NC / 2 + jl];
-                const float4 h0 = *reinterpret_cast<const float4*>(hcur + k * TS);
-                const float4 h1 = *reinterpret_cast<const float4*>(hcur + k * TS + 4);
-                a0[0] = fmaf(w0, h0.x, a0[0]); a0[1] = fmaf(w0, h0.y, a0[1]); a0[2] = fmaf(w0, h0.z, a0[2]); a0[3] = fmaf(w0, h0.w, a0[3]);
-                a0[4] = fmaf(w0, h1.x, a0[4]); a0[5] = fmaf(w0, h1.y, a0[5]); a0[6] = fmaf(w0, h1.z, a0[6]); a0[7] = fmaf(w0, h1.w, a0[7]);
-                a1[0] = fmaf(w1, h0.x, a1[0]); a1[1] = fmaf(w1, h0.y, a1[1]); a1[2] = fmaf(w1, h0.z, a1[2]); a1[3] = fmaf(w1, h0.w, a1[3]);
-                a1[4] = fmaf(w1, h1.x, a1[4]); a1[5] = fmaf(w1, h1.y, a1[5]); a1[6] = fmaf(w1, h1.z, a1[6]); a1[7] = fmaf(w1, h1.w, a1[7]);
-            }
+                const unsigned long long w00 = pack_f32x2(w0, w0), w11 = pack_f32x2(w1, w1);
+                const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(hcur + k * TS);
+                const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(hcur + k * TS + 4);
+                a0[0] = fma_f32x2(w00, h0.x, a0[0]); a0[1] = fma_f32x2(w00, h0.y, a0[1]);
+                a0[2] = fma_f32x2(w00, h1.x, a0[2]); a0[3] = fma_f32x2(w00, h1.y, a0[3]);
+                a1[0] = fma_f32x2(w11, h0.x, a1[0]); a1[1] = fma_f32x2(w11, h0.y, a1[1]);
+                a1[2] = fma_f32x2(w11, h1.x, a1[2]); a1[3] = fma_f32x2(w11, h1.y, a1[3]);
+            };
+            // group g takes k = g, g + 4, g + 8, ...: H / 4 iterations for every group (a compile-time count when HT
+            // is given: no peeled alignment iterations) plus one more for the first H % 4 groups
+            int k = grp;
+#pragma unroll 4
+            for (int i = 0; i < (H / CL_KGROUPS) / 4 * 4; ++i, k += CL_KGROUPS) body(k);
+#pragma unroll
+            for (int i = (H / CL_KGROUPS) / 4 * 4; i < H / CL_KGROUPS; ++i, k += CL_KGROUPS) body(k);
+            if (grp < H % CL_KGROUPS) body(k);
             float* z = zp + grp * TS * NC;
 #pragma unroll
-            for (int s = 0; s < TS; ++s) { z[s * NC + jl] = a0[s]; z[s * NC + NC / 2 + jl] = a1[s]; }
+            for (int s = 0; s < TS / 2; ++s) {
+                float lo, hi;
+                unpack_f32x2(a0[s], lo, hi);
+                z[(2 * s) * NC + jl] = lo; z[(2 * s + 1) * NC + jl] = hi;
+                unpack_f32x2(a1[s], lo, hi);
+                z[(2 * s) * NC + NC / 2 + jl] = lo; z[(2 * s + 1) * NC + NC / 2 + jl] = hi;
+            }
         }
+        // next step's input projections: issued AFTER the product (in flight during the gate phase and the exchange,
+        // consumed a whole step later) — issued before it, the loads shared scoreboard slots with the product's
+        // shared-memory loads and stalled it
+        fetch(t + 1, gnx);
         __syncthreads();
         float* hnext = hs + (cur ^ 1) * H * TS;
         const uint32_t peer_full = cur ? peer_full0 : peer_full1;          // the peer's full[cur ^ 1]
@@ -546,23 +567,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         mb_wait(&full, (uint32_t)it & 1u);                   // the peer's half
         // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
         if (t > 0) {
-            float acc[TS];
-#pragma unroll
-            for (int s = 0; s < TS; ++s) acc[s] = 0.f;
             if (live2) {
+                unsigned long long acc[TS / 2];
+#pragma unroll
+                for (int s = 0; s < TS / 2; ++s) acc[s] = 0ull;
                 const int j0 = jq * Hh;                      // 4H / 8 gate rows per group
 #pragma unroll 5
                 for (int j = 0; j < Hh; ++j) {
                     const float w = Wb[(j0 + j) * Hh + kk2];
-                    const float4 d0 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS);
-                    const float4 d1 = *reinterpret_cast<const float4*>(dzs + (j0 + j) * TS + 4);
-                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
-                    acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
-                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
-                    acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                    const unsigned long long ww = pack_f32x2(w, w);
+                    const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(dzs + (j0 + j) * TS);
+                    const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(dzs + (j0 + j) * TS + 4);
+                    acc[0] = fma_f32x2(ww, d0.x, acc[0]); acc[1] = fma_f32x2(ww, d0.y, acc[1]);
+                    acc[2] = fma_f32x2(ww, d1.x, acc[2]); acc[3] = fma_f32x2(ww, d1.y, acc[3]);
                 }
 #pragma unroll
-                for (int s = 0; s < TS; ++s) part[(jq * TS + s) * Hh + kk2] = acc[s];
+                for (int s = 0; s < TS / 2; ++s) {
+                    float lo, hi;
+                    unpack_f32x2(acc[s], lo, hi);
+                    part[(jq * TS + 2 * s) * Hh + kk2] = lo;
+                    part[(jq * TS + 2 * s + 1) * Hh + kk2] = hi;
+                }
             }
             __syncthreads();                                 // every thread has finished reading dzs
             if (tid == 0) mb_arrive_remote(peer_free);       // ... so the peer may send its next step's gradients
