@@ -269,6 +269,9 @@ int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bi
                          float* pooled /* optional [B,C]: global spatial max (ref: nn.MaxPool2d(14,14), model:302) fused
                                           into the operand pass; precision == 1 only, else NULL */,
                          float* bank, void* stream);
+int mgnns_imgbank_fwd_tc_capped(const float* fmap, const float* weight, const float* bias,
+                                int B, int C, int P, int O, int precision, float* workspace, float* pooled,
+                                float* bank, int max_ctas /* 0 = every SM */, void* stream);
 int mgnns_imgbank_dw_tc(const float* fmap, const float* gbank, int B, int C, int P, int O,
                         int precision, float* gW, void* stream);
 /* same, on at most max_ctas SMs (0 = all): the weight gradient is not needed before the optimizer (engine:850-851), so

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mgnns_count_row_nnz_i32": (c_int, [P, c_int, c_int, c_int, P, P]),
     "mgnns_count_fill_csr_i32": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
     "mgnns_imgbank_fwd_tc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "mgnns_imgbank_fwd_tc_capped": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P]),
     "mgnns_imgbank_dw_tc": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "mgnns_imgbank_dw_tc_capped": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
     "mgnns_linear_tc_workspace": (c_int64, [c_int, c_int, c_int64, c_int, c_int]),

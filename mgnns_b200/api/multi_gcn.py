@@ -378,6 +378,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
         streams = self._branch_streams(5)
         if streams is None:
             # one stream, the reference's order (ref: model:444-546)
+            ops.set_concurrent_streams(False)
             text_feature = text_gcn()
             text_memory_bank = text_bank()
             img_object_memory_bank, object_x_attention = object_channel()
@@ -395,6 +396,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
             # stream: in the backward pass it is fed late (through the text-bank stacks), and on a shared stream it
             # would sit in front of the image-bank weight gradient, which is ready much earlier.
             main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab) = streams
+            ops.set_concurrent_streams(True)                # stays on: the backward pass of this forward forks the same way
             for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab):
                 side.wait_stream(main)                      # fork: after everything already enqueued on main
             # The LSTM recurrence is latency-bound and leaves most SMs idle, while the image-bank kernels are

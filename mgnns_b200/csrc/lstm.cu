@@ -30,6 +30,12 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // tanh through one accurate expf: 1 - 2/(1+e^{2x}); |error| ~1e-7, saturates correctly at +-inf
 __device__ __forceinline__ float tanhf_(float x) { return 1.f - 2.f / (1.f + expf(2.f * x)); }
 
+// fast forms for the cluster kernels' gate phase (ex2.approx + approximate reciprocal, ~2 ulp each: 1e-7 relative,
+// against the 1e-4 / 1e-5 bound of the LSTM parity test): the accurate expf and IEEE division cost ~25 instructions per
+// gate, and the gate phase was 22 % of a recurrence step
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
 constexpr int KCH = 16;      // W_hh elements fetched per thread before they are consumed (memory-level parallelism)
 
 // WT[k][j] = Whh[j][k]   (j = gate*H + unit)
@@ -303,6 +309,7 @@ __device__ __forceinline__ void mb_arrive_remote(uint32_t remote_bar) {
 // eight sequences per thread, as before), the four partial sums meet in shared memory, and the gate phase has one
 // (unit, sequence) pair per thread instead of two in sequence.
 constexpr int CL_KGROUPS = 4;
+__device__ long long* g_lstm_dbg = nullptr;   // profiling aid: per-phase cycle sums of CTA (0,0), thread 0 and thread 608
 
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
@@ -369,7 +376,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     Gin gin, gnx;
     fetch(0, gin);
     int cur = 0;
+    long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 608)) ? g_lstm_dbg : nullptr;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
     for (int t = 0; t < tile_len; ++t) {
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+        if (dbg) c0 = clock64();
         if (tid == 0) mb_expect_tx(&full[cur ^ 1], step_bytes);
         if (zlive) {
             // two columns x eight sequences per thread; sequences in pairs, one FFMA2 per (column, pair) and k
@@ -408,8 +419,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         // next step's input projections: issued AFTER the product (in flight during the gate phase and the exchange,
         // consumed a whole step later) — issued before it, the loads shared scoreboard slots with the product's
         // shared-memory loads and stalled it
+        if (dbg) c1 = clock64();
         fetch(t + 1, gnx);
         __syncthreads();
+        if (dbg) c2 = clock64();
         float* hnext = hs + (cur ^ 1) * H * TS;
         const uint32_t peer_full = cur ? peer_full0 : peer_full1;          // the peer's full[cur ^ 1]
         float sv[7];                                         // i, f, g, o, c, h_prev, h of the thread's pair
@@ -425,9 +438,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                     for (int kg = 0; kg < CL_KGROUPS; ++kg) acc += zp[(kg * TS + p_s) * NC + g * Hh + p_u];
                     zg[g] = acc;
                 }
-                const float ig = sigmoidf_(zg[0]), fg = sigmoidf_(zg[1]), gg = tanhf_(zg[2]), og = sigmoidf_(zg[3]);
+                const float ig = sigmoid_fast(zg[0]), fg = sigmoid_fast(zg[1]), gg = tanh_fast(zg[2]), og = sigmoid_fast(zg[3]);
                 cst = fg * cst + ig * gg;
-                hnew = og * tanhf_(cst);
+                hnew = og * tanh_fast(cst);
                 sv[0] = ig; sv[1] = fg; sv[2] = gg; sv[3] = og; sv[4] = cst; sv[5] = hold; sv[6] = hnew;
             }
             hnext[u_glob * TS + p_s] = hnew;
@@ -444,14 +457,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         // Hh * TS / 4 threads then copy to the peer 16 bytes each), the peer's half (its bytes counted on
         // full[cur ^ 1]).  The peer overwrites hs[cur] only in ITS step t + 1, i.e. after it has received every byte of
         // this step from here — which is sent after every thread's last read of hs[cur].
+        if (dbg) c3 = clock64();
         __syncthreads();
+        if (dbg) c4 = clock64();
         if (tid < npairs / 4) {
             const float* src = hnext + rank * Hh * TS + 4 * tid;
             st_async_f32x4(cl_map(src, peer), *reinterpret_cast<const float4*>(src), peer_full);
         }
         mb_wait(&full[cur ^ 1], (uint32_t)(t >> 1) & 1u);
+        if (dbg) {
+            c5 = clock64();
+            ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; ph[5] += 1;
+        }
         cur ^= 1;
         gin = gnx;
+    }
+    if (dbg) {
+        long long* o = dbg + (tid == 0 ? 0 : 8);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = ph[i];
     }
     cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
 }
@@ -540,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 const float ig = cur_sv.ig, fg = cur_sv.fg, gg = cur_sv.gg, og = cur_sv.og;
                 const float c = cur_sv.c, cprev = cur_sv.cprev;
                 const float dhv = cur_sv.dy + dh[p_s * Hh + p_u];
-                const float tc = tanhf_(c);
+                const float tc = tanh_fast(c);
                 const float dct = dcs + dhv * og * (1.f - tc * tc);
                 dz[0] = dct * gg * ig * (1.f - ig);
                 dz[1] = dct * cprev * fg * (1.f - fg);
@@ -619,6 +643,11 @@ extern "C" int mgnns_lstm_prep_whh(const float* whh, float* wt4, int H, void* st
     lstm_prep_whh_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(whh, wt4, H);
     MG_LAUNCH_CHECK("lstm_prep_whh");
     return 0;
+}
+
+// profiling aid (not part of the public header): cycle sums per phase of the forward kernel's CTA (0,0) go to buf[16]
+extern "C" int mgnns_lstm_debug_buffer(long long* buf) {
+    return cudaMemcpyToSymbol(g_lstm_dbg, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
 }
 
 extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, const int32_t* tiles, int n_tiles,

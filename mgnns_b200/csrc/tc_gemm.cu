@@ -501,6 +501,15 @@ using namespace mgnns::tc;
 // global spatial max of the feature map, fused into the operand pass.
 extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, const float* bias, int B, int C, int P, int O,
                                     int precision, float* workspace, float* pooled, float* bank, void* stream) {
+    return mgnns_imgbank_fwd_tc_capped(fmap, weight, bias, B, C, P, O, precision, workspace, pooled, bank, 0, stream);
+}
+
+// max_ctas > 0 caps the persistent grid: the kernel's CTAs take a whole SM each (225 KB of shared memory), so a grid
+// on every SM blocks every small kernel of a concurrent stream for its whole duration; a few SMs left free keep the
+// latency-bound chains of the training step moving
+extern "C" int mgnns_imgbank_fwd_tc_capped(const float* fmap, const float* weight, const float* bias, int B, int C, int P,
+                                           int O, int precision, float* workspace, float* pooled, float* bank, int max_ctas,
+                                           void* stream) {
     MG_REQUIRE(B >= 0 && C >= 32 && P >= 1 && O >= 1, "imgbank_fwd_tc: bad dimensions");
     MG_REQUIRE(C % KCHUNK == 0, "imgbank_fwd_tc: C=%d must be a multiple of 32", C);
     MG_REQUIRE(O <= Geo<FWD>::BN && O % 4 == 0, "imgbank_fwd_tc: O=%d must be <= 304 and a multiple of 4", O);
@@ -549,7 +558,7 @@ extern "C" int mgnns_imgbank_fwd_tc(const float* fmap, const float* weight, cons
     p.n_items = (int)items;
     p.groups = 1; p.samples_per_group = 1;
     p.pooled_ord = reinterpret_cast<uint32_t*>(pooled);
-    if (int rc = precision ? launch<FWD, true>(ma, mb, mbl, p, st) : launch<FWD, false>(ma, mb, mbl, p, st)) return rc;
+    if (int rc = precision ? launch<FWD, true>(ma, mb, mbl, p, st, max_ctas) : launch<FWD, false>(ma, mb, mbl, p, st, max_ctas)) return rc;
     if (pooled) {
         const int64_t n = (int64_t)B * C;
         ordered_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.pooled_ord, n);

@@ -1023,6 +1023,35 @@ def _imgbank_check(fmap, weight, bias):
     return fmap, weight, bias
 
 
+# SMs the persistent image-bank kernels leave free while the model runs its chains on several streams (their CTAs
+# take a whole SM each, so a grid on every SM stalls every small kernel of the other streams for ~0.8 ms).  Measured
+# on the B=512 training step: 0 -> 7.46 ms, 4 / 8 / 16 -> 7.56, 24 -> 7.62: the small kernels do start earlier on the
+# reserved SMs but crawl there (200 us instead of 15), and everything downstream waits for the image banks anyway.
+_IMGBANK_RESERVE = int(os.environ.get("MGNNS_IMGBANK_RESERVE_SMS", "0"))
+_sm_counts = {}
+
+
+def _imgbank_ctas():
+    """CTA cap for the image-bank kernels: all SMs on a single-stream run, SMs - reserve inside the stream graph."""
+    if not _concurrent["on"] or _IMGBANK_RESERVE <= 0:
+        return 0
+    dev = torch.cuda.current_device()
+    n = _sm_counts.get(dev)
+    if n is None:
+        n = _sm_counts[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return max(n - _IMGBANK_RESERVE, 1)
+
+
+_concurrent = {"on": False}
+
+
+def set_concurrent_streams(on: bool) -> bool:
+    """Tell the ops that other chains of the model are running on other streams (Multi_GCN_Multihead_Att.forward with
+    branch_streams, and the backward pass of such a forward)."""
+    prev, _concurrent["on"] = _concurrent["on"], bool(on)
+    return prev
+
+
 def _imgbank_impl(fmap, weight, bias):
     fmap, weight, bias = _imgbank_check(fmap, weight, bias)
     B, C, P = fmap.shape
@@ -1037,8 +1066,9 @@ def _imgbank_impl(fmap, weight, bias):
         # recomputed there (empty placeholder here)
         ws = torch.empty((2 * O * C,), device=fmap.device, dtype=torch.float32)
         with _timed("imgbank_fwd"):
-            _check(_lib.mgnns_imgbank_fwd_tc(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
-                                             prec, ws.data_ptr(), pooled.data_ptr(), bank.data_ptr(), s), "imgbank_fwd_tc")
+            _check(_lib.mgnns_imgbank_fwd_tc_capped(fmap.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, C, P, O,
+                                                    prec, ws.data_ptr(), pooled.data_ptr(), bank.data_ptr(), _imgbank_ctas(),
+                                                    s), "imgbank_fwd_tc")
         return bank, pooled, torch.empty((0,), device=fmap.device, dtype=torch.int32)
     argmax = torch.empty((B, C), device=fmap.device, dtype=torch.int32)
     with _timed("rowmax"):
@@ -1102,7 +1132,8 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
             if _tc_ok(C, P, O, 320):
                 with _timed("imgbank_dw"):
                     _check(_lib.mgnns_imgbank_dw_tc_capped(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
-                                                           _PRECISIONS[_precision], gw.data_ptr(), max_ctas, _stream()),
+                                                           _PRECISIONS[_precision], gw.data_ptr(),
+                                                           max_ctas or _imgbank_ctas(), _stream()),
                            "imgbank_dw_tc")
             else:
                 with _timed("imgbank_dw"):
