@@ -18,6 +18,9 @@ from .text_gcn import Model as Text_GCN_Model
 
 # forward schedule knob (see forward()): 1 = the scene channel's image-bank kernel waits for the last LSTM layer's launch
 _PLACE_AFTER_LAST_LAYER = os.environ.get('MGNNS_PLACE_AFTER_LAST_LAYER', '1') == '1'
+# side streams of forward() that run at normal priority: the two image channels (persistent image-bank kernels +
+# image-query stacks); the LSTM / text-bank stacks / label channels are the critical path and get priority -1
+_NORMAL_PRIORITY = (1, 2) if os.environ.get('MGNNS_STREAM_PRIORITIES', '1') == '1' else (1, 2, 3, 4, 5)
 _PKG_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data', 'label_graphs.npz')
 
 # ref: models/Multi_GCN_Multihead_att.py:20-27 loads the label GloVe matrix at import time from a path
@@ -375,7 +378,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 x = layer(q=x, k=bank, v=bank, mask=mask)[0]
             return x
 
-        streams = self._branch_streams(5)
+        streams = self._branch_streams(6)
         if streams is None:
             # one stream, the reference's order (ref: model:444-546)
             ops.set_concurrent_streams(False)
@@ -395,9 +398,9 @@ class Multi_GCN_Multihead_Att(nn.Module):
             # The label-graph half of an image channel (pooled -> label GCN scores -> label attention) has its own
             # stream: in the backward pass it is fed late (through the text-bank stacks), and on a shared stream it
             # would sit in front of the image-bank weight gradient, which is ready much earlier.
-            main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab) = streams
+            main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2) = streams
             ops.set_concurrent_streams(True)                # stays on: the backward pass of this forward forks the same way
-            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab):
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2):
                 side.wait_stream(main)                      # fork: after everything already enqueued on main
             # The LSTM recurrence is latency-bound and leaves most SMs idle, while the image-bank kernels are
             # persistent and take every SM they can get: the image channels therefore start once the LSTM's first
@@ -444,16 +447,22 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 s_txt.wait_event(ev_obj)
                 img_object_text = stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank,
                                         text_mask)
-            main.wait_event(ev_bank)
-            main.wait_event(ev_plc)
-            img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank, text_mask)
-            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab):
+            # both text-bank stacks sit between the LSTM forward and the LSTM backward — the critical path of the step —
+            # so both run on high-priority streams (as do the label channels that produce their queries): their small
+            # kernels get SM slots ahead of the image-query stacks and the deferred weight gradients
+            with torch.cuda.stream(s_txt2):
+                s_txt2.wait_event(ev_bank)
+                s_txt2.wait_event(ev_plc)
+                img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank,
+                                       text_mask)
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2):
                 main.wait_stream(side)                      # join
             # tensors that crossed streams: tell the caching allocator about every stream that read them
             for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt,)),
-                               (text_memory_bank, (main,)), (place_x_attention, (main,)),
+                               (text_memory_bank, (s_txt2,)), (place_x_attention, (s_txt2,)),
                                (text_img_object, (main,)), (text_img_place, (main,)), (img_object_text, (main,)),
-                               (text_mask, (s_txt,)), (query, (s_obj_lab, s_plc_lab))):
+                               (img_place_text, (main,)),
+                               (text_mask, (s_txt, s_txt2)), (query, (s_obj_lab, s_plc_lab))):
                 for r in readers:
                     t.record_stream(r)
 
@@ -477,7 +486,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
         if pool is None or pool[0] != dev or len(pool[1]) < n:
             # the first side stream carries the LSTM chain (latency-bound, leaves most SMs idle): high priority, so
             # its CTAs are placed first and the dynamically scheduled tensor-core kernels fill the rest of the GPU
-            pool = (dev, [torch.cuda.Stream(device=dev, priority=(-1 if i == 0 else 0)) for i in range(n)])
+            pool = (dev, [torch.cuda.Stream(device=dev, priority=(0 if i in _NORMAL_PRIORITY else -1)) for i in range(n)])
             self.__dict__['_branch_pool'] = pool
             # gc1/gc2 are shared by the object and place channels: their AccumulateGrad nodes see gradients from
             # two streams by design
