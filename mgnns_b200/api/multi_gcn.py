@@ -20,7 +20,7 @@ from .text_gcn import Model as Text_GCN_Model
 _PLACE_AFTER_LAST_LAYER = os.environ.get('MGNNS_PLACE_AFTER_LAST_LAYER', '1') == '1'
 # side streams of forward() that run at normal priority: the two image channels (persistent image-bank kernels +
 # image-query stacks); the LSTM / text-bank stacks / label channels are the critical path and get priority -1
-_NORMAL_PRIORITY = (1, 2) if os.environ.get('MGNNS_STREAM_PRIORITIES', '1') == '1' else (1, 2, 3, 4, 5)
+_NORMAL_PRIORITY = tuple(int(x) for x in os.environ.get('MGNNS_NORMAL_PRIORITY_STREAMS', '1,2').split(',') if x != '')
 _PKG_DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'data', 'label_graphs.npz')
 
 # ref: models/Multi_GCN_Multihead_att.py:20-27 loads the label GloVe matrix at import time from a path
@@ -378,7 +378,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 x = layer(q=x, k=bank, v=bank, mask=mask)[0]
             return x
 
-        streams = self._branch_streams(6)
+        streams = self._branch_streams(7)
         if streams is None:
             # one stream, the reference's order (ref: model:444-546)
             ops.set_concurrent_streams(False)
@@ -398,9 +398,9 @@ class Multi_GCN_Multihead_Att(nn.Module):
             # The label-graph half of an image channel (pooled -> label GCN scores -> label attention) has its own
             # stream: in the backward pass it is fed late (through the text-bank stacks), and on a shared stream it
             # would sit in front of the image-bank weight gradient, which is ready much earlier.
-            main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2) = streams
+            main, (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2, s_txt3) = streams
             ops.set_concurrent_streams(True)                # stays on: the backward pass of this forward forks the same way
-            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2):
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2, s_txt3):
                 side.wait_stream(main)                      # fork: after everything already enqueued on main
             # The LSTM recurrence is latency-bound and leaves most SMs idle, while the image-bank kernels are
             # persistent and take every SM they can get: the image channels therefore start once the LSTM's first
@@ -443,8 +443,12 @@ class Multi_GCN_Multihead_Att(nn.Module):
             with torch.cuda.stream(s_plc):
                 s_plc.wait_event(ev_tf)
                 text_img_place = stack(self.text_img_place_multi_head_att, text_feature, img_place_memory_bank)
-            with torch.cuda.stream(s_txt):
-                s_txt.wait_event(ev_obj)
+            # NOT on s_txt, the stream that produced the text bank: in the backward pass autograd sums the four gradients
+            # of the bank on that stream, each sum waiting for its producer — a stack queued behind those sums would
+            # wait for the OTHER stack's backward (measured: the two text-bank stacks ran back to back, 0.85 ms)
+            with torch.cuda.stream(s_txt3):
+                s_txt3.wait_event(ev_bank)
+                s_txt3.wait_event(ev_obj)
                 img_object_text = stack(self.img_object_text_multi_head_att, object_x_attention, text_memory_bank,
                                         text_mask)
             # both text-bank stacks sit between the LSTM forward and the LSTM backward — the critical path of the step —
@@ -455,14 +459,14 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 s_txt2.wait_event(ev_plc)
                 img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank,
                                        text_mask)
-            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2):
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2, s_txt3):
                 main.wait_stream(side)                      # join
             # tensors that crossed streams: tell the caching allocator about every stream that read them
-            for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt,)),
-                               (text_memory_bank, (s_txt2,)), (place_x_attention, (s_txt2,)),
+            for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt3,)),
+                               (text_memory_bank, (s_txt2, s_txt3)), (place_x_attention, (s_txt2,)),
                                (text_img_object, (main,)), (text_img_place, (main,)), (img_object_text, (main,)),
                                (img_place_text, (main,)),
-                               (text_mask, (s_txt, s_txt2)), (query, (s_obj_lab, s_plc_lab))):
+                               (text_mask, (s_txt2, s_txt3)), (query, (s_obj_lab, s_plc_lab))):
                 for r in readers:
                     t.record_stream(r)
 
