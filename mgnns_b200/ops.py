@@ -105,7 +105,8 @@ class _timed:
 # join_deferred() issues job i on its own side stream behind (its inputs, gate i + a few microseconds): the
 # recurrence has been handed its SMs when the heavy kernel starts, which then fills the remaining ones.  Everything
 # is stream dependencies, so a CUDA-graph capture records exactly this order.
-_defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": []}
+_defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": [], "before_heavy": []}
+_HEAVY_AFTER_TEXT = os.environ.get("MGNNS_HEAVY_AFTER_TEXT", "0") == "1"   # measured: 7.44 vs 7.36 ms without
 _GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
 _DEFER_SMALL = os.environ.get("MGNNS_DEFER_SMALL", "1") == "1"     # also defer the small (M = batch) weight gradients
 
@@ -178,17 +179,26 @@ def _drop_gate(device):
     _defer_state["gates"].append(ev)
 
 
+def _before_heavy(device):
+    """Work enqueued so far on the current stream must be finished before any heavy deferred job starts."""
+    if _defer_state["enabled"] and _HEAVY_PLAN and _HEAVY_AFTER_TEXT:
+        _defer_state["before_heavy"].append(torch.cuda.current_stream(device).record_event())
+
+
 def join_deferred():
     """Issue the gated heavy jobs, join every deferred stream into the current one and accumulate the results into
     .grad (call after loss.backward(), before anything reads the gradients)."""
     heavy, _defer_state["heavy"] = _defer_state["heavy"], []
     gates, _defer_state["gates"] = _defer_state["gates"], []
+    before, _defer_state["before_heavy"] = _defer_state["before_heavy"], []
     joined = set(_defer_state["gate_streams"])       # helper streams rejoin even when no heavy job waited on them
     _defer_state["gate_streams"] = []
     for i, (fn, inputs, params, ready) in enumerate(heavy):
         dev = inputs[0].device
         side = _defer_stream(dev, 'heavy%d' % (i % 2))
         side.wait_event(ready)
+        for ev in before:
+            side.wait_event(ev)
         max_ctas, gate = _HEAVY_PLAN[min(i, len(_HEAVY_PLAN) - 1)]
         if gates and gate >= 0:
             side.wait_event(gates[min(gate, len(gates) - 1)])
@@ -790,6 +800,10 @@ def _text_backward(ctx, g):
                                       edge_w_c.data_ptr(), edge_w_c.numel(), pmi_rowptr.data_ptr(),
                                       pmi_col.data_ptr(), _ptr(pmi_eid), int(apply_relu), out.data_ptr(),
                                       g.data_ptr(), g_h.data_ptr(), g_w.data_ptr(), _stream()), "text_maxagg_bwd")
+    # The text-GCN backward becomes ready together with the image-bank weight gradients (both hang off the
+    # image-query stacks' backward) and needs few SMs for ~0.13 ms; started behind two persistent kernels that hold
+    # every SM it ran last, 1.6 ms later, as the tail of the whole step.  Heavy deferred jobs therefore go behind it.
+    _before_heavy(g.device)
     return None, g_h, g_w.view_as(edge_w), None, None, None, None, None, None
 
 
@@ -1028,6 +1042,7 @@ def _imgbank_check(fmap, weight, bias):
 # on the B=512 training step: 0 -> 7.46 ms, 4 / 8 / 16 -> 7.56, 24 -> 7.62: the small kernels do start earlier on the
 # reserved SMs but crawl there (200 us instead of 15), and everything downstream waits for the image banks anyway.
 _IMGBANK_RESERVE = int(os.environ.get("MGNNS_IMGBANK_RESERVE_SMS", "0"))
+_DW_CHUNKS = int(os.environ.get("MGNNS_DW_CHUNKS", "1"))   # measured 1 / 2 / 4 / 8 chunks: 7.34 / 7.45 / 7.49 / 7.87 ms per step
 _sm_counts = {}
 
 
@@ -1130,11 +1145,18 @@ def _imgbank_backward(ctx, g_bank, g_pooled, g_argmax):
             gw = torch.zeros_like(weight)
             r = _pick_reduce(B)
             if _tc_ok(C, P, O, 320):
+                # Optional (MGNNS_DW_CHUNKS > 1): cut the product into sample chunks (it accumulates into gw with atomics
+                # anyway) so that kernels of other streams waiting for an SM get in at the chunk boundaries — the LSTM
+                # weight gradients and the embedding backward otherwise run as a 0.45 ms tail after the last
+                # image-bank kernel.  Measured: the per-launch cost of the chunks outweighs the overlap (default 1).
+                chunks = min(_DW_CHUNKS, B) if _concurrent["on"] else 1
                 with _timed("imgbank_dw"):
-                    _check(_lib.mgnns_imgbank_dw_tc_capped(fmap3.data_ptr(), g_bank.data_ptr(), B, C, P, O,
-                                                           _PRECISIONS[_precision], gw.data_ptr(),
-                                                           max_ctas or _imgbank_ctas(), _stream()),
-                           "imgbank_dw_tc")
+                    for ci in range(chunks):
+                        b0, b1 = B * ci // chunks, B * (ci + 1) // chunks
+                        _check(_lib.mgnns_imgbank_dw_tc_capped(fmap3[b0:b1].data_ptr(), g_bank[b0:b1].data_ptr(), b1 - b0,
+                                                               C, P, O, _PRECISIONS[_precision], gw.data_ptr(),
+                                                               max_ctas or _imgbank_ctas(), _stream()),
+                               "imgbank_dw_tc")
             else:
                 with _timed("imgbank_dw"):
                     gemm_raw(1, 1, O, C, P, g_bank, O, P * O, fmap3, P, C * P, gw, C, 0, batch=B, reduce=r, accumulate=1)
