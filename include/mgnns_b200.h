@@ -367,6 +367,21 @@ int mgnns_clip_adam_f32(float* g, int64_t n, const int64_t* seg_g, const int64_t
 
 
 /* ---------------------------------------------------------------------------
+ * Text memory bank glue around the compacted-token LSTM.
+ * ref: models/Multi_GCN_Multihead_att.py:366-398 (self.embedding; pad_packed_sequence(total_length) -> zero rows past
+ * each text's length)
+ *   pad_rows_fwd   bank[b,t,:] = t < lens[b] ? y[offsets[b]+t,:] : 0          (bank [B,L,F], y [N,F], F % 4 == 0)
+ *   pad_rows_bwd   gy[offsets[b]+t,:] = gbank[b,t,:] for t < lens[b]           (other rows of gy untouched)
+ *   embedding_bwd  gw[tokens[i],:] += g[i,:] for tokens[i] != padding_idx      (gw [V,E] initialised by the caller)
+ * ------------------------------------------------------------------------- */
+int mgnns_pad_rows_fwd(const float* y, const int32_t* offsets, const int32_t* lens, int B, int L, int F,
+                       float* bank, void* stream);
+int mgnns_pad_rows_bwd(const float* gbank, const int32_t* offsets, const int32_t* lens, int B, int L, int F,
+                       float* gy, void* stream);
+int mgnns_embedding_bwd(const int64_t* tokens, const float* g, int64_t n, int E, int64_t padding_idx, int64_t V,
+                        float* gw, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Gradient all-reduce over NVLink peer memory (one kernel, capturable in a CUDA graph).
  * ref: SURVEY 8e / engine/Multi_GCN_Multihead_Att_engine.py:847-851 — the one collective of the path sits between
  * loss.backward() and clip_grad_norm_; the reference itself is single-GPU.

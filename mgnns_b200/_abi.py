@@ -63,6 +63,9 @@ SIGNATURES = {
     "mgnns_sqnorm_f32": (c_int, [P, c_int64, P, P]),
     "mgnns_clip_adam_f32": (c_int, [P, c_int64, P, P, P, P, c_int, P, P, P, P, c_double, c_double, c_double, c_double, P, P]),
     "mgnns_delay_ns": (c_int, [c_int, P]),
+    "mgnns_pad_rows_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "mgnns_pad_rows_bwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "mgnns_embedding_bwd": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, P, P]),
     "mgnns_p2p_flag_bytes": (c_int, []),
     "mgnns_p2p_alloc": (c_int, [c_int64, P]),
     "mgnns_p2p_free": (c_int, [P]),

@@ -258,11 +258,19 @@ class Multi_GCN_Multihead_Att(nn.Module):
         dev = self.embedding.weight.device
         plan = self.make_text_plan(text_lens, max_text_len)
         tokens = text.to(dev).reshape(-1).index_select(0, plan.tok_idx)
-        text_embed = self.embedding(tokens)                                        # [N, emb]
+        fused_glue = (self.embedding.weight.shape[1] % 4 == 0 and self.bi_hidden_size % 4 == 0
+                      and self.embedding.max_norm is None and not self.embedding.sparse)
+        if fused_glue:
+            text_embed = ops.embedding_rows(self.embedding.weight, tokens, self.embedding.padding_idx)   # [N, emb]
+        else:
+            text_embed = self.embedding(tokens)
         y = ops.packed_bilstm(self.lstm, text_embed, plan, self.training, after_first_projection)   # [N, 2H]
-        # scatter back to the padded layout; plan padding rows land in one dummy row that is sliced off
-        memory_bank = y.new_zeros(batch_size * max_text_len + 1, y.shape[1]).index_copy(0, plan.flat_idx, y)
-        memory_bank = memory_bank[:batch_size * max_text_len].view(batch_size, max_text_len, y.shape[1])
+        if fused_glue:
+            memory_bank = ops.pad_text_bank(y, plan, batch_size, max_text_len)     # one pass: valid rows + zero padding
+        else:
+            # scatter back to the padded layout; plan padding rows land in one dummy row that is sliced off
+            memory_bank = y.new_zeros(batch_size * max_text_len + 1, y.shape[1]).index_copy(0, plan.flat_idx, y)
+            memory_bank = memory_bank[:batch_size * max_text_len].view(batch_size, max_text_len, y.shape[1])
         assert memory_bank.size() == torch.Size([batch_size, max_text_len, self.bi_hidden_size])
         if not return_last_state:
             return memory_bank

@@ -1528,6 +1528,70 @@ class _LstmInputProjection(torch.autograd.Function):
         return (gx, *weight_grads())
 
 
+class _PadTextBank(torch.autograd.Function):
+    """bank[b, t, :] = y[offsets[b] + t, :] for t < lens[b], zero rows after (ref: pad_packed_sequence(total_length),
+    model:386-390) in one pass over the bank; backward gathers the valid rows."""
+
+    @staticmethod
+    def forward(ctx, y, offsets, lens, B, L):
+        y = _f32c(y, "y")
+        F = y.shape[1]
+        bank = torch.empty((B, L, F), device=y.device, dtype=torch.float32)
+        _check(_lib.mgnns_pad_rows_fwd(y.data_ptr(), offsets.data_ptr(), lens.data_ptr(), B, L, F, bank.data_ptr(), _stream()),
+               "pad_rows_fwd")
+        ctx.save_for_backward(offsets, lens)
+        ctx.dims = (y.shape[0], B, L, F)
+        return bank
+
+    @staticmethod
+    def backward(ctx, g):
+        offsets, lens = ctx.saved_tensors
+        N, B, L, F = ctx.dims
+        g = _f32c(g, "grad_bank")
+        gy = torch.zeros((N, F), device=g.device, dtype=torch.float32)
+        _check(_lib.mgnns_pad_rows_bwd(g.data_ptr(), offsets.data_ptr(), lens.data_ptr(), B, L, F, gy.data_ptr(), _stream()),
+               "pad_rows_bwd")
+        return gy, None, None, None, None
+
+
+def pad_text_bank(y, plan, B, L):
+    """Compact LSTM output [capacity, F] -> zero-padded bank [B, L, F] (F % 4 == 0)."""
+    _need_cuda(y)
+    if y.shape[1] % 4 != 0:
+        raise RuntimeError("mgnns pad_text_bank: feature width must be a multiple of 4")
+    return _PadTextBank.apply(y, plan.offsets, plan.lens, int(B), int(L))
+
+
+class _EmbeddingRows(torch.autograd.Function):
+    """weight[tokens] (ref: self.embedding(text), model:377) with the table's gradient as ONE scatter-add launch
+    (rows equal to padding_idx receive no gradient, as nn.Embedding(padding_idx=...) does)."""
+
+    @staticmethod
+    def forward(ctx, weight, tokens, padding_idx):
+        ctx.save_for_backward(tokens)
+        ctx.meta = (weight.shape, -1 if padding_idx is None else int(padding_idx))
+        return weight.index_select(0, tokens)
+
+    @staticmethod
+    def backward(ctx, g):
+        (tokens,) = ctx.saved_tensors
+        (V, E), pad = ctx.meta
+        g = _f32c(g, "grad")
+        gw = torch.zeros((V, E), device=g.device, dtype=torch.float32)
+        _check(_lib.mgnns_embedding_bwd(tokens.data_ptr(), g.data_ptr(), tokens.numel(), E, pad, V, gw.data_ptr(), _stream()),
+               "embedding_bwd")
+        return gw, None, None
+
+
+def embedding_rows(weight, tokens, padding_idx=None):
+    _need_cuda(weight, tokens)
+    if weight.dtype != torch.float32 or weight.dim() != 2 or weight.shape[1] % 4 != 0 or not weight.is_contiguous():
+        raise RuntimeError("mgnns embedding_rows: weight must be contiguous float32 [V, E] with E % 4 == 0")
+    if tokens.dtype != torch.int64 or tokens.dim() != 1 or not tokens.is_contiguous():
+        raise RuntimeError("mgnns embedding_rows: tokens must be contiguous int64 [N]")
+    return _EmbeddingRows.apply(weight, tokens, padding_idx)
+
+
 def packed_bilstm(lstm: torch.nn.LSTM, x_compact: torch.Tensor, plan: LstmPlan, training: bool, after_first_projection=None):
     """Multi-layer bidirectional LSTM over compacted tokens with nn.LSTM's parameters (same names, same
     math as torch's packed-sequence path, inter-layer dropout included).  Returns [N, 2H]."""

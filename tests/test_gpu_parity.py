@@ -1322,3 +1322,40 @@ def test_cpu_tensors_are_rejected(dev):
         torch.ops.mgnns.mm(torch.randn(3, 3), torch.randn(3, 3), None, False, False, 0, 0.0)
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.mgnns.add_layernorm(torch.randn(3, 8), None, torch.ones(8), torch.zeros(8), 1e-6)
+
+
+def test_text_bank_glue_kernels_match_torch(dev, ops):
+    """mgnns_pad_rows_fwd/bwd and mgnns_embedding_bwd against the torch formulation they replace (new_zeros + index_copy
+    into the padded bank; nn.Embedding's dense backward with padding_idx): values bit-equal (pure data movement),
+    table gradient to summation order; lengths include 1, the maximum, and a text longer than L (clamped)."""
+    torch.manual_seed(3)
+    B, L, F, V, E = 9, 100, 300, 57, 300
+    lens = torch.tensor([1, 100, 7, 130, 2, 55, 100, 3, 18])
+    plan = ops.LstmPlan(lens, L, dev, capacity=512)
+    assert int(plan.N) == int(lens.clamp(max=L).sum())
+    y = torch.randn(plan.capacity, F, device=dev)
+    y[plan.N:] = 0
+    y1 = y.clone().requires_grad_()
+    bank = ops.pad_text_bank(y1, plan, B, L)
+    y2 = y.clone().requires_grad_()
+    ref = y2.new_zeros(B * L + 1, F).index_copy(0, plan.flat_idx, y2)[:B * L].view(B, L, F)
+    assert torch.equal(bank, ref)
+    for b in range(B):
+        assert bank[b, min(int(lens[b]), L):].abs().max().item() == 0 if int(lens[b]) < L else True
+    g = torch.randn_like(bank)
+    bank.backward(g)
+    ref.backward(g)
+    assert torch.equal(y1.grad, y2.grad)
+    # embedding rows: tokens with repeats and the padding index
+    emb = torch.nn.Embedding(V, E, padding_idx=0).to(dev)
+    tokens = torch.randint(0, V, (700,), device=dev)
+    tokens[::13] = 0
+    w1 = emb.weight.detach().clone().requires_grad_()
+    out = ops.embedding_rows(w1, tokens, 0)
+    ref = emb(tokens)
+    assert torch.equal(out, ref)
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g)
+    close(w1.grad, emb.weight.grad, 1e-5, 1e-6)
+    assert w1.grad[0].abs().max().item() == 0
