@@ -217,3 +217,33 @@ def test_launch_list_summariser(tmp_path, capsys):
         sys.argv = argv
     out = capsys.readouterr().out
     assert 'launches [3, 6)' in out and '3 launches' in out and 'mgnns::gemm_ffma_kernel' in out
+
+
+def test_heavy_plan_parser_and_flat_gradient_alloc_hook():
+    """Host logic of the captured step: MGNNS_HEAVY_PLAN entries (CTA cap / gate per deferred heavy job) and the
+    FlatGradients allocation hook that lets the flat gradient buffer live in peer-mapped memory."""
+    import torch
+    from mgnns_b200 import ops
+    from mgnns_b200.optim import FlatGradients
+    assert ops._parse_heavy_plan("g0,g1") == [(0, 0), (0, 1)]
+    assert ops._parse_heavy_plan("c100,g0") == [(100, -1), (0, 0)]
+    assert ops._parse_heavy_plan("c74g1") == [(74, 1)]
+    assert ops._parse_heavy_plan("off") is None
+    with pytest.raises(ValueError):
+        ops._parse_heavy_plan("x3")
+    ps = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(2, 2))]
+    for p in ps[:2]:
+        p.grad = torch.randn_like(p)
+    asked = []
+
+    def alloc(n):
+        asked.append(n)
+        return torch.zeros(n)
+    fg = FlatGradients(ps, alloc=alloc)
+    assert asked == [16 + 8] and len(fg.params) == 2 and fg.offsets == [0, 16]      # 15 -> 16, 7 -> 8 floats; no-grad param left out
+    want = [p.grad.clone() for p in ps[:2]]
+    fg.pack()
+    for p, w, v in zip(ps[:2], want, fg.views):
+        assert torch.equal(p.grad, w) and p.grad.data_ptr() == v.data_ptr()
+    with pytest.raises(RuntimeError):
+        FlatGradients(ps, alloc=lambda n: torch.zeros(n + 4))
