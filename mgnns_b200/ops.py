@@ -105,7 +105,7 @@ class _timed:
 # join_deferred() issues job i on its own side stream behind (its inputs, gate i + a few microseconds): the
 # recurrence has been handed its SMs when the heavy kernel starts, which then fills the remaining ones.  Everything
 # is stream dependencies, so a CUDA-graph capture records exactly this order.
-_defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": [], "before_heavy": []}
+_defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": [], "before_heavy": [], "lazy": []}
 _HEAVY_AFTER_TEXT = os.environ.get("MGNNS_HEAVY_AFTER_TEXT", "0") == "1"   # measured: 7.44 vs 7.36 ms without
 _GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
 _DEFER_SMALL = os.environ.get("MGNNS_DEFER_SMALL", "1") == "1"     # also defer the small (M = batch) weight gradients
@@ -140,7 +140,11 @@ def _defer_stream(device, which=0):
     return s
 
 
-def _run_deferred(fn, inputs, params, heavy=False):
+_LAZY_SMALL = os.environ.get("MGNNS_LAZY_SMALL", "0") == "1"
+_LSTM_BWD_AFTER_IMAGE = os.environ.get("MGNNS_LSTM_BWD_AFTER_IMAGE", "0") == "1"   # measured: 7.32 vs 7.31 ms (no gain)
+
+
+def _run_deferred(fn, inputs, params, heavy=False, lazy=False):
     """Enqueue fn() -> list of gradient tensors (one per entry of `params`, None allowed) on the side stream, after
     everything enqueued so far on the current stream; the (param, grad) pairs are applied by join_deferred().
     heavy=True: fn takes the CTA cap of its persistent kernel; only queued here (with an "inputs ready" event) and
@@ -149,6 +153,10 @@ def _run_deferred(fn, inputs, params, heavy=False):
     cur = torch.cuda.current_stream(dev)
     if heavy:
         _defer_state["heavy"].append((fn, inputs, params, cur.record_event()))
+        return
+    if lazy and _LAZY_SMALL:
+        # issued by join_deferred() behind the first gate: off the SMs while the attention stacks' backward chains run
+        _defer_state["lazy"].append((fn, inputs, params, cur.record_event(), _defer_stream(dev, ('side', cur.cuda_stream))))
         return
     # one side stream per origin stream: the four attention stacks' weight gradients do not queue behind each other
     side = _defer_stream(dev, ('side', cur.cuda_stream))
@@ -204,6 +212,20 @@ def join_deferred():
             side.wait_event(gates[min(gate, len(gates) - 1)])
         with torch.cuda.stream(side):
             grads = fn(max_ctas)
+        for t in inputs:
+            t.record_stream(side)
+        joined.add((dev, side))
+        for p, g in zip(params, grads):
+            if p is not None and g is not None:
+                _defer_state["pending"].append((p, g))
+    lazy, _defer_state["lazy"] = _defer_state["lazy"], []
+    for fn, inputs, params, ready, side in lazy:
+        dev = inputs[0].device
+        side.wait_event(ready)
+        if gates:
+            side.wait_event(gates[0])
+        with torch.cuda.stream(side):
+            grads = fn()
         for t in inputs:
             t.record_stream(side)
         joined.add((dev, side))
@@ -449,7 +471,7 @@ def _mm_backward(ctx, g):
     if ((need_w or need_bias) and _defer_state["enabled"] and _DEFER_SMALL and w_leaf.is_leaf
             and (bias_leaf is None or bias_leaf.is_leaf)):
         # a parameter's gradient is not needed before the optimizer: off the backward chain, onto the side stream
-        _run_deferred(weight_grads, (g, a), (w_leaf if need_w else None, bias_leaf if need_bias else None))
+        _run_deferred(weight_grads, (g, a), (w_leaf if need_w else None, bias_leaf if need_bias else None), lazy=True)
     elif need_w or need_bias:
         gb, gbias = weight_grads()
     return ga, gb, gbias, None, None, None, None
@@ -538,7 +560,7 @@ def _head_mm_backward(ctx, g):
 
     if ctx.needs_input_grad[1]:
         if _defer_state["enabled"] and _DEFER_SMALL and ctx.leaves[0].is_leaf:
-            _run_deferred(weight_grads, (g, x), ctx.leaves)
+            _run_deferred(weight_grads, (g, x), ctx.leaves, lazy=True)
         else:
             gw = weight_grads()[0]
     return gx, gw, None, None
@@ -1457,6 +1479,14 @@ def _lstm_backward(ctx, gy, ggates, gc, ghp):
     gy = _f32c(gy, "grad_y")
     N = gy.shape[0]
     dG = torch.zeros((N, 8 * H), device=gy.device, dtype=torch.float32)
+    if _LSTM_BWD_AFTER_IMAGE and _defer_state["enabled"] and not _defer_state["gates"]:
+        # Optional (measured, no gain): hold the first (top-layer) recurrence of the backward pass until the image-query
+        # stacks' backward has delivered the image banks' gradients (the "ready" events of the queued heavy jobs;
+        # autograd runs those nodes before this one), so that its 256 whole-SM CTAs do not land in the middle of that
+        # chain of small kernels.
+        cur = torch.cuda.current_stream(gy.device)
+        for job in _defer_state["heavy"]:
+            cur.wait_event(job[3])
     _drop_gate(gy.device)                  # gated heavy jobs (image-bank weight gradients) start just behind this launch
     with _timed("lstm_rec_bwd"):
         _check(_lib.mgnns_lstm_rec_bwd(offsets.data_ptr(), lens.data_ptr(), tiles.data_ptr(), ctx.n_tiles, H,
