@@ -414,9 +414,16 @@ class Multi_GCN_Multihead_Att(nn.Module):
             # persistent and take every SM they can get: the image channels therefore start once the LSTM's first
             # input projection is done, i.e. when the recurrence is being launched on its high-priority stream, so
             # the recurrence gets its SMs first and the (dynamically scheduled) tensor-core kernels fill the rest.
-            lstm_ready = []
+            lstm_ready, helpers = [], []
+
+            def before_recurrence():
+                ev, helper = ops.delayed_event(dev_main, 'fwd_gate%d' % len(lstm_ready))
+                lstm_ready.append(ev)
+                if helper is not None:
+                    helpers.append(helper)
+            dev_main = text_mask.device
             with torch.cuda.stream(s_txt):
-                text_memory_bank = text_bank(lambda: lstm_ready.append(s_txt.record_event()))
+                text_memory_bank = text_bank(before_recurrence)
                 ev_bank = s_txt.record_event()
 
             def image_channel(s_img, s_lab, gates, trunk, feature, linear, inp, adj, attention, linear_5, x_linear, attr):
@@ -467,7 +474,7 @@ class Multi_GCN_Multihead_Att(nn.Module):
                 s_txt2.wait_event(ev_plc)
                 img_place_text = stack(self.img_place_text_multi_head_att, place_x_attention, text_memory_bank,
                                        text_mask)
-            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2, s_txt3):
+            for side in (s_txt, s_obj, s_plc, s_obj_lab, s_plc_lab, s_txt2, s_txt3, *helpers):
                 main.wait_stream(side)                      # join
             # tensors that crossed streams: tell the caching allocator about every stream that read them
             for t, readers in ((text_feature, (s_obj, s_plc)), (object_x_attention, (s_txt3,)),

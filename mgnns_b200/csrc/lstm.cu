@@ -11,6 +11,7 @@
 // Forward saves the post-activation gates, the cell state and h_{t-1} per token; backward walks the
 // same tiles in reverse time and emits the pre-activation gradients dG, from which the caller gets
 // dW_ih / dx / db (GEMMs over the compact matrices) and dW_hh = dG^T . Hprev.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mgnns {
@@ -314,38 +315,32 @@ __device__ long long* g_lstm_dbg = nullptr;   // profiling aid: per-phase cycle 
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_fwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ G, const float* __restrict__ wt_f, const float* __restrict__ wt_r,
-    float* __restrict__ Y, float* __restrict__ gates, float* __restrict__ csave, float* __restrict__ hprev) {
+    float* __restrict__ Y, float* __restrict__ gates, float* __restrict__ csave, float* __restrict__ hprev,
+    int n_tiles, int* __restrict__ tile_ctr_f, int* __restrict__ tile_ctr_r) {
     extern __shared__ __align__(16) float sm[];
     const int H = HT ? HT : plan.H, Hh = H / 2, NC = 4 * Hh;          // NC = gate columns owned by this CTA
     float* Wsm = sm;                                         // [H][NC]
     float* hs = Wsm + H * NC;                                // [2][H][TS]
     float* zp = hs + 2 * H * TS;                             // [CL_KGROUPS][TS][NC]
     __shared__ int s_off[TS], s_len[TS];
+    __shared__ int s_tile;
     __shared__ __align__(8) uint64_t full[2];                // full[b]: the peer's half of hs[b] has landed
-    const int dir = blockIdx.y, tile = blockIdx.x >> 1;
+    const int dir = blockIdx.y;
     const uint32_t rank = cl_rank(), peer = rank ^ 1u;
     const float* __restrict__ WT = dir ? wt_r : wt_f;        // [H][4H]
+    int* tile_ctr = dir ? tile_ctr_r : tile_ctr_f;
     const int tid = threadIdx.x;
-    if (tid < TS) {
-        int s = plan.tiles[tile * TS + tid];
-        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
-        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
-    }
     if (tid == 0) {
         mb_init(&full[0], 1);
         mb_init(&full[1], 1);
         mb_fence_init();
     }
+    // W_hh is loaded ONCE per cluster: the clusters are persistent and draw (length-sorted) tiles from a queue
     for (int i = tid; i < H * NC; i += CL_THREADS) {
         const int k = i / NC, lc = i - k * NC, g = lc / Hh, uu = lc - g * Hh;
         Wsm[i] = WT[(int64_t)k * (4 * H) + g * H + rank * Hh + uu];
     }
-    for (int i = tid; i < 2 * H * TS; i += CL_THREADS) hs[i] = 0.f;
-    __syncthreads();
-    int tile_len = 0;
-#pragma unroll
-    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
-    cl_sync();                                               // peer's buffers / mbarriers are initialised before any remote store
+    cl_sync();          // both CTAs are running and their mbarriers are initialised before any remote access
 
     // z-phase mapping: four groups of 160 threads split the k range; each thread owns two columns
     const int grp = tid / 160, jl = tid % 160;
@@ -354,9 +349,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     const int npairs = Hh * TS;
     const bool p_ok = tid < npairs;
     const int p_s = p_ok ? tid / Hh : 0, p_u = p_ok ? tid % Hh : 0;
+    const uint32_t step_bytes = (uint32_t)(npairs * sizeof(float));     // what the peer sends per step
+    const uint32_t peer_full0 = cl_map(&full[0], peer), peer_full1 = cl_map(&full[1], peer);
+    const uint32_t peer_tile = cl_map(&s_tile, peer);
+    const int u_glob = rank * Hh + p_u;
+    long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 608)) ? g_lstm_dbg : nullptr;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    int gstep = 0;                                           // steps done by this cluster over all its tiles
+  for (;;) {
+    // ---- next tile of the queue (longest first); both CTAs of the cluster must take the same one -----------------
+    if (rank == 0 && tid == 0) {
+        const int tl = atomicAdd(tile_ctr, 1);
+        s_tile = tl;
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer_tile), "r"(tl) : "memory");
+    }
+    cl_sync();          // the tile number has landed on both sides; every exchange of the previous tile is complete
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    if (tid < TS) {
+        int s = plan.tiles[tile * TS + tid];
+        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
+    }
+    {   // h_0 = 0: the buffer the first step reads
+        float* h0 = hs + (gstep & 1) * H * TS;
+        for (int i = tid; i < H * TS; i += CL_THREADS) h0[i] = 0.f;
+    }
+    __syncthreads();
+    int tile_len = 0;
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
     const int p_len = s_len[p_s], p_off = s_off[p_s];
     float cst = 0.f;
-    // input projections of one step for the thread's pair; the NEXT step's are fetched at the top of a step, so their
+    // input projections of one step for the thread's pair; the NEXT step's are fetched one step ahead, so their
     // L2 latency is off the per-step critical path
     struct Gin { float g[4]; int64_t row; bool on; };
     auto fetch = [&](int t, Gin& gi) {
@@ -370,15 +395,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         for (int g = 0; g < 4; ++g) gi.g[g] = __ldg(g_in + g * H);
         gi.on = true;
     };
-    const uint32_t step_bytes = (uint32_t)(npairs * sizeof(float));     // what the peer sends per step
-    const uint32_t peer_full0 = cl_map(&full[0], peer), peer_full1 = cl_map(&full[1], peer);
-    const int u_glob = rank * Hh + p_u;
     Gin gin, gnx;
     fetch(0, gin);
-    int cur = 0;
-    long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 608)) ? g_lstm_dbg : nullptr;
-    long long ph[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < tile_len; ++t) {
+    for (int t = 0; t < tile_len; ++t, ++gstep) {
+        const int cur = gstep & 1;
         long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
         if (dbg) c0 = clock64();
         if (tid == 0) mb_expect_tx(&full[cur ^ 1], step_bytes);
@@ -464,14 +484,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
             const float* src = hnext + rank * Hh * TS + 4 * tid;
             st_async_f32x4(cl_map(src, peer), *reinterpret_cast<const float4*>(src), peer_full);
         }
-        mb_wait(&full[cur ^ 1], (uint32_t)(t >> 1) & 1u);
+        mb_wait(&full[cur ^ 1], (uint32_t)(gstep >> 1) & 1u);
         if (dbg) {
             c5 = clock64();
             ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; ph[5] += 1;
         }
-        cur ^= 1;
         gin = gnx;
     }
+  }
     if (dbg) {
         long long* o = dbg + (tid == 0 ? 0 : 8);
 #pragma unroll
@@ -485,7 +505,8 @@ constexpr int CL_JGROUPS = 8;        // backward phase 2: the 4H gate rows are c
 template <int HT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_rec_bwd_cl_kernel(
     LstmPlan plan, const float* __restrict__ dY, const float* __restrict__ gates, const float* __restrict__ csave,
-    const float* __restrict__ whh_f, const float* __restrict__ whh_r, float* __restrict__ dG) {
+    const float* __restrict__ whh_f, const float* __restrict__ whh_r, float* __restrict__ dG,
+    int n_tiles, int* __restrict__ tile_ctr_f, int* __restrict__ tile_ctr_r) {
     extern __shared__ __align__(16) float sm[];
     const int H = HT ? HT : plan.H, Hh = H / 2;
     float* Wb = sm;                                          // [4H][Hh]: W_hh columns of this CTA's hidden units
@@ -493,43 +514,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
     float* part = dzs + 4 * H * TS;                          // [CL_JGROUPS][TS][Hh]
     float* dh = part + CL_JGROUPS * TS * Hh;                 // [TS][Hh]
     __shared__ int s_off[TS], s_len[TS];
+    __shared__ int s_tile;
     __shared__ __align__(8) uint64_t full, freeb;            // full: the peer's gate gradients of this step have landed;
                                                              // freeb: the peer has finished reading what was sent to it
-    const int dir = blockIdx.y, tile = blockIdx.x >> 1;
+    const int dir = blockIdx.y;
     const uint32_t rank = cl_rank(), peer = rank ^ 1u;
     const float* __restrict__ W = dir ? whh_r : whh_f;       // [4H][H]
+    int* tile_ctr = dir ? tile_ctr_r : tile_ctr_f;
     const int tid = threadIdx.x;
-    if (tid < TS) {
-        int s = plan.tiles[tile * TS + tid];
-        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
-        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
-    }
     if (tid == 0) {
         mb_init(&full, 1);
         mb_init(&freeb, 1);
         mb_fence_init();
     }
+    // W_hh is loaded ONCE per cluster: the clusters are persistent and draw (length-sorted) tiles from a queue
     for (int i = tid; i < 4 * H * Hh; i += CL_THREADS) {
         const int j = i / Hh, kk = i - j * Hh;
         Wb[i] = W[(int64_t)j * H + rank * Hh + kk];
+    }
+    cl_sync();          // both CTAs are running and their mbarriers are initialised before any remote access
+
+    // phase-1 mapping: one (unit, sequence) pair per thread
+    const int npairs = Hh * TS;
+    const bool p_ok = tid < npairs;
+    const int p_s = p_ok ? tid / Hh : 0, p_u = p_ok ? tid % Hh : 0;
+    const int u_glob = rank * Hh + p_u;
+    // phase-2 mapping: thread (kk, one of eight groups of gate rows)
+    const int kk2 = tid % 80, jq = tid / 80;
+    const bool live2 = kk2 < Hh;
+    const uint32_t step_bytes = (uint32_t)(4 * npairs * sizeof(float));  // what the peer sends per step
+    const uint32_t peer_full = cl_map(&full, peer), peer_free = cl_map(&freeb, peer);
+    const uint32_t peer_tile = cl_map(&s_tile, peer);
+    int gstep = 0;                                           // steps done by this cluster over all its tiles
+  for (;;) {
+    // ---- next tile of the queue (longest first); both CTAs of the cluster must take the same one -----------------
+    if (rank == 0 && tid == 0) {
+        const int tl = atomicAdd(tile_ctr, 1);
+        s_tile = tl;
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer_tile), "r"(tl) : "memory");
+    }
+    cl_sync();          // the tile number has landed on both sides; every exchange of the previous tile is complete
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    if (tid < TS) {
+        int s = plan.tiles[tile * TS + tid];
+        s_off[tid] = s >= 0 ? plan.offsets[s] : 0;
+        s_len[tid] = s >= 0 ? plan.lens[s] : 0;
     }
     for (int i = tid; i < TS * Hh; i += CL_THREADS) dh[i] = 0.f;
     __syncthreads();
     int tile_len = 0;
 #pragma unroll
     for (int s = 0; s < TS; ++s) tile_len = max(tile_len, s_len[s]);
-    cl_sync();
-
-    // phase-1 mapping: one (unit, sequence) pair per thread
-    const int npairs = Hh * TS;
-    const bool p_ok = tid < npairs;
-    const int p_s = p_ok ? tid / Hh : 0, p_u = p_ok ? tid % Hh : 0;
     const int p_len = s_len[p_s], p_off = s_off[p_s];
-    const int u_glob = rank * Hh + p_u;
     float dcs = 0.f;
-    // phase-2 mapping: thread (kk, one of eight groups of gate rows)
-    const int kk2 = tid % 80, jq = tid / 80;
-    const bool live2 = kk2 < Hh;
     // saved forward tensors of one time step for the thread's pair; the NEXT step's are fetched while this step's
     // exchange and product run, so their L2 latency is off the per-step critical path
     struct Saved { float ig, fg, gg, og, c, cprev, dy; int64_t row; bool on; };
@@ -550,12 +588,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         sv.row = row;
         sv.on = true;
     };
-    const uint32_t step_bytes = (uint32_t)(4 * npairs * sizeof(float));  // what the peer sends per step
-    const uint32_t peer_full = cl_map(&full, peer), peer_free = cl_map(&freeb, peer);
     Saved cur_sv, nxt_sv;
     fetch(tile_len - 1, cur_sv);
-    for (int t = tile_len - 1; t >= 0; --t) {
-        const int it = tile_len - 1 - t;                     // 0-based step count
+    for (int t = tile_len - 1; t >= 0; --t, ++gstep) {
         if (tid == 0) mb_expect_tx(&full, step_bytes);
         // ---- phase 1: gate gradients for this CTA's hidden units -------------------------------------
         float dz[4] = {0.f, 0.f, 0.f, 0.f};
@@ -582,13 +617,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
         fetch(t - 1, nxt_sv);
         __syncthreads();                                     // own half of dzs: four contiguous blocks of Hh * TS floats
         if (p_ok) {
-            // the peer's dzs may be overwritten once it has finished phase 2 of the previous step
-            if (it > 0) mb_wait(&freeb, (uint32_t)(it - 1) & 1u);
+            // the peer's dzs may be overwritten once it has finished reading the previous step's (it says so every step)
+            if (gstep > 0) mb_wait(&freeb, (uint32_t)(gstep - 1) & 1u);
             const int g = tid / (npairs / 4), r = tid - g * (npairs / 4);
             const float* src = dzs + (g * H + rank * Hh) * TS + 4 * r;
             st_async_f32x4(cl_map(src, peer), *reinterpret_cast<const float4*>(src), peer_full);
         }
-        mb_wait(&full, (uint32_t)it & 1u);                   // the peer's half
+        mb_wait(&full, (uint32_t)gstep & 1u);                // the peer's half
         // ---- phase 2: dh_{t-1}[s][k] = sum_j W_hh[j][k] dz[s][j] for this CTA's k half ------------------
         if (t > 0) {
             if (live2) {
@@ -622,10 +657,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1) lstm_
                 dh[tid] = v;
             }
             __syncthreads();                                 // dh complete before phase 1 of the next step reads it
+        } else {
+            // last step of the tile: nobody reads dzs, but the peer's next send (first step of its next tile) still
+            // waits for this step's "free" — every step signals exactly once
+            __syncthreads();
+            if (tid == 0) mb_arrive_remote(peer_free);
         }
         cur_sv = nxt_sv;
     }
+  }
     cl_sync();          // neither CTA leaves (and frees its shared memory) while the other may still write into it
+}
+
+// Persistent clusters: `lstm_clusters` per direction (2 CTAs = 2 SMs each) draw the length-sorted tiles from a queue.
+// One cluster per tile (the earlier scheme) put 256 whole-SM CTAs on the GPU at every launch: for ~100 us nothing else
+// ran (timeline: every other stream of the training step stalled), and each of those CTAs first loaded its 180 KB half
+// of W_hh for what was mostly a handful of time steps.  The longest tile (100 steps) bounds the kernel either way; 20
+// clusters per direction finish the other 63 tiles of a B = 512 batch (~1,100 steps in total) well inside that time and
+// leave 68 SMs to the rest of the step.  MGNNS_LSTM_CLUSTERS overrides.
+static int lstm_clusters(int n_tiles) {
+    static int n = 0;
+    if (!n) {
+        const char* v = getenv("MGNNS_LSTM_CLUSTERS");
+        n = v ? atoi(v) : 20;
+        if (n < 1) n = 20;
+    }
+    return n_tiles < n ? n_tiles : n;
+}
+
+}  // namespace mgnns
+namespace mgnns { namespace tc { int* next_tile_counter(cudaStream_t st); } }
+namespace mgnns {
+
+// two queue heads (forward / reverse direction), zeroed on the launch stream (capture-aware slots, tc_gemm.cu)
+static int lstm_tile_counters(cudaStream_t st, int** cf, int** cr) {
+    *cf = tc::next_tile_counter(st);
+    *cr = tc::next_tile_counter(st);
+    return (*cf && *cr) ? 0 : 1;
 }
 
 static size_t lstm_cl_fwd_smem(int H) { return sizeof(float) * ((size_t)H * 2 * H + 2 * H * TS + (size_t)CL_KGROUPS * TS * 2 * H); }
@@ -667,10 +735,13 @@ extern "C" int mgnns_lstm_rec_fwd(const int32_t* offsets, const int32_t* lens, c
             MG_REQUIRE(e == cudaSuccess, "lstm_rec_fwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
             configured = true;
         }
+        int *cf = nullptr, *cr = nullptr;
+        const int ncl = lstm_clusters(n_tiles);
+        MG_REQUIRE(lstm_tile_counters(as_stream(stream), &cf, &cr) == 0, "lstm_rec_fwd: cannot set up the tile counters");
         if (H == 150)      // the reference's hidden size (entry: --hidden_size 150)
-            lstm_rec_fwd_cl_kernel<150><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+            lstm_rec_fwd_cl_kernel<150><<<dim3(2 * ncl, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev, n_tiles, cf, cr);
         else
-            lstm_rec_fwd_cl_kernel<0><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev);
+            lstm_rec_fwd_cl_kernel<0><<<dim3(2 * ncl, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, G, wt4_f, wt4_r, Y, gates, csave, hprev, n_tiles, cf, cr);
         MG_LAUNCH_CHECK("lstm_rec_fwd_cl");
         return 0;
     }
@@ -695,10 +766,13 @@ extern "C" int mgnns_lstm_rec_bwd(const int32_t* offsets, const int32_t* lens, c
             MG_REQUIRE(e == cudaSuccess, "lstm_rec_bwd: cannot reserve shared memory: %s", cudaGetErrorString(e));
             configured = true;
         }
+        int *cf = nullptr, *cr = nullptr;
+        const int ncl = lstm_clusters(n_tiles);
+        MG_REQUIRE(lstm_tile_counters(as_stream(stream), &cf, &cr) == 0, "lstm_rec_bwd: cannot set up the tile counters");
         if (H == 150)
-            lstm_rec_bwd_cl_kernel<150><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+            lstm_rec_bwd_cl_kernel<150><<<dim3(2 * ncl, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG, n_tiles, cf, cr);
         else
-            lstm_rec_bwd_cl_kernel<0><<<dim3(2 * n_tiles, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG);
+            lstm_rec_bwd_cl_kernel<0><<<dim3(2 * ncl, 2), CL_THREADS, smem, as_stream(stream)>>>(plan, dY, gates, csave, whh_f, whh_r, dG, n_tiles, cf, cr);
         MG_LAUNCH_CHECK("lstm_rec_bwd_cl");
         return 0;
     }

@@ -107,7 +107,7 @@ class _timed:
 # is stream dependencies, so a CUDA-graph capture records exactly this order.
 _defer_state = {"enabled": False, "streams": {}, "pending": [], "heavy": [], "gates": [], "gate_streams": [], "before_heavy": [], "lazy": []}
 _HEAVY_AFTER_TEXT = os.environ.get("MGNNS_HEAVY_AFTER_TEXT", "0") == "1"   # measured: 7.44 vs 7.36 ms without
-_GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "8000"))
+_GATE_DELAY_NS = int(os.environ.get("MGNNS_GATE_DELAY_NS", "30000"))
 _DEFER_SMALL = os.environ.get("MGNNS_DEFER_SMALL", "1") == "1"     # also defer the small (M = batch) weight gradients
 
 
@@ -169,6 +169,20 @@ def _run_deferred(fn, inputs, params, heavy=False, lazy=False):
     for p, g in zip(params, grads):
         if p is not None and g is not None:
             _defer_state["pending"].append((p, g))
+
+
+def delayed_event(device, key):
+    """Event that fires _GATE_DELAY_NS after everything enqueued so far on the current stream has finished (the delay
+    runs on a helper stream named by `key`): for releasing a persistent kernel of another stream just BEHIND a
+    latency-critical launch that is about to be enqueued here (a few small nodes — weight transposes, counter memsets —
+    still sit in front of that launch).  The helper stream is returned too: the caller joins it."""
+    ev = torch.cuda.current_stream(device).record_event()
+    if _GATE_DELAY_NS <= 0:
+        return ev, None
+    helper = _defer_stream(device, key)
+    helper.wait_event(ev)
+    _check(_lib.mgnns_delay_ns(_GATE_DELAY_NS, helper.cuda_stream), "delay")
+    return helper.record_event(), helper
 
 
 def _drop_gate(device):
