@@ -249,6 +249,7 @@ def join_deferred():
     pending, _defer_state["pending"] = _defer_state["pending"], []
     for dev, side in joined:
         torch.cuda.current_stream(dev).wait_stream(side)
+    acc_dst, acc_src = [], []
     for p, g in pending:
         g.record_stream(torch.cuda.current_stream(g.device))
         if p.grad is None:
@@ -256,8 +257,15 @@ def join_deferred():
         else:
             # in place, as AccumulateGrad does: a never-stepped parameter keeps ONE gradient buffer that accumulates
             # across steps, and a captured graph must keep writing to that same buffer on every replay
-            with torch.no_grad():
-                p.grad.add_(g)
+            acc_dst.append(p.grad)
+            acc_src.append(g)
+    if acc_dst:
+        with torch.no_grad():
+            if len({id(t) for t in acc_dst}) == len(acc_dst):
+                torch._foreach_add_(acc_dst, acc_src)       # one multi-tensor launch instead of ~20 tiny ones at the tail
+            else:                                           # the same buffer more than once: keep the order explicit
+                for d, g in zip(acc_dst, acc_src):
+                    d.add_(g)
 
 
 # ----------------------------------------------------------------------------- helpers
