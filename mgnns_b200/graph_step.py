@@ -37,7 +37,10 @@ class GraphedTrainStep:
         # Default capacity: this batch's token count with 12.5 % headroom, rounded up to 1024 rows (the LSTM's
         # many-row products run over `capacity` rows, so B*L — the safe upper bound — would cost 6x on TumEmo-shaped
         # text); a later batch with more tokens makes update_lengths() grow the plan and re-capture (see there).
-        cap = plan_capacity if plan_capacity is not None else min(batch['text'].shape[0] * L, ((n + n // 8 + 1023) // 1024) * 1024)
+        # (world > 1: 25 % headroom — growing the plan re-captures the step, which runs collectives, so it cannot happen
+        # on one rank alone; update_lengths() raises instead, see there)
+        room = n // 8 if world_size == 1 else n // 4
+        cap = plan_capacity if plan_capacity is not None else min(batch['text'].shape[0] * L, ((n + room + 1023) // 1024) * 1024)
         self.lens_key = batch['lens']                      # identity of this tensor keys the plan cache
         self.plan = model.make_text_plan(self.lens_key, L, capacity=cap)
         self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -164,6 +167,14 @@ class GraphedTrainStep:
         (one-off cost of a few eager steps; `recaptures` counts them) instead of failing mid-training."""
         L = self.batch['text'].shape[1]
         n = int(lens_cpu.clamp(max=L).sum())
+        if n > self.plan.capacity and self.world > 1:
+            # Re-capturing runs warm-up steps with the gradient all-reduce in them; a rank that did so alone would
+            # leave the others waiting in a collective (NCCL) or trip the 4 s barrier time-out of the peer-memory
+            # kernel.  Fail loudly instead: the caller picks a capacity every rank can live with.
+            raise RuntimeError("GraphedTrainStep.update_lengths: %d valid tokens exceed the plan capacity %d on this rank; "
+                               "with world_size > 1 the step cannot be re-captured by one rank alone — construct it with "
+                               "plan_capacity=batch*max_len (always safe) or a bound that holds for every batch"
+                               % (n, self.plan.capacity))
         if n > self.plan.capacity:
             cap = min(self.batch['text'].shape[0] * L, ((max(n, self.plan.capacity * 3 // 2) + 1023) // 1024) * 1024)
             torch.cuda.synchronize()
