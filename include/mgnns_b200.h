@@ -391,7 +391,7 @@ int mgnns_embedding_bwd(const int64_t* tokens, const float* g, int64_t n, int E,
  *   mgnns_allreduce_p2p_f32       buf_r[i] = scale * sum_q buf_q[i] on every rank r (bit-identical results on all
  *                                 ranks); bufs / flags are HOST arrays of `world` device pointers, own allocation at
  *                                 index `rank`; n % 4 == 0; all ranks must launch it the same number of times
- *   mgnns_p2p_error               1 if a cross-GPU barrier of this rank ever timed out (4 s), -1 on a CUDA error
+ *   mgnns_p2p_error               1 if a cross-GPU barrier of this rank ever timed out (20 s), -1 on a CUDA error
  * ------------------------------------------------------------------------- */
 int mgnns_p2p_flag_bytes(void);
 int mgnns_p2p_alloc(int64_t bytes, void** out);

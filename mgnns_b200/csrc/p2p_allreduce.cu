@@ -17,7 +17,7 @@
 // Barriers are per CTA index (CTA c only ever touches sub-chunk c of every slice, on every rank), built from
 // st.release.sys / ld.acquire.sys on flag words in peer memory with monotonically increasing epochs kept on the
 // device, so replaying a captured graph needs no host-side state.  A rank reduces each element of its slice exactly
-// once and in rank order, so all ranks end up with bit-identical sums.  A spin that lasts longer than 4 s sets an
+// once and in rank order, so all ranks end up with bit-identical sums.  A spin that lasts longer than 20 s sets an
 // error word instead of hanging the GPU.
 #include <string.h>
 #include "common.cuh"
@@ -70,7 +70,7 @@ __device__ __forceinline__ void p2p_barrier(const P2PParams& p, int c, uint32_t 
         const unsigned long long t0 = global_ns();
         // epochs only grow; the signed difference also survives the 32-bit wrap
         while ((int32_t)(ld_acquire_sys(mine) - val) < 0) {
-            if (global_ns() - t0 > 4000000000ull) {
+            if (global_ns() - t0 > 20000000000ull) {
                 p.flag[p.rank][P2P_ERR_OFF] = 1u;
                 break;
             }

@@ -169,7 +169,7 @@ class GraphedTrainStep:
         n = int(lens_cpu.clamp(max=L).sum())
         if n > self.plan.capacity and self.world > 1:
             # Re-capturing runs warm-up steps with the gradient all-reduce in them; a rank that did so alone would
-            # leave the others waiting in a collective (NCCL) or trip the 4 s barrier time-out of the peer-memory
+            # leave the others waiting in a collective (NCCL) or trip the 20 s barrier time-out of the peer-memory
             # kernel.  Fail loudly instead: the caller picks a capacity every rank can live with.
             raise RuntimeError("GraphedTrainStep.update_lengths: %d valid tokens exceed the plan capacity %d on this rank; "
                                "with world_size > 1 the step cannot be re-captured by one rank alone — construct it with "
