@@ -101,16 +101,24 @@ class GraphedTrainStep:
             fo = self.flat_opt if (self.flat_opt is not None and self.flat_opt is not True) else None
             if fo is not None:
                 self._fg = fo.grads
+                self.use_p2p = self.use_p2p and self._fg.peer is not None
             elif self.use_p2p:
-                from .p2p import PeerAllReduce
+                from .p2p import PeerAllReduce, PeerMemoryUnavailable
                 dev = self.batch['text'].device
                 made = []
 
                 def alloc(n):
                     made.append(PeerAllReduce(n, dev))       # rendezvous: every rank gets here in its first step
                     return made[0].flat
-                self._fg = FlatGradients(self.model.parameters(), alloc=alloc)
-                self._fg.peer = made[0]
+                try:
+                    self._fg = FlatGradients(self.model.parameters(), alloc=alloc)
+                    self._fg.peer = made[0]
+                except PeerMemoryUnavailable as exc:         # raised on every rank alike: all fall back to NCCL together
+                    import warnings
+                    warnings.warn("mgnns_b200: peer-memory all-reduce unavailable (%s); using the NCCL all-reduce between "
+                                  "two captured halves" % exc)
+                    self.use_p2p = False
+                    self._fg = FlatGradients(self.model.parameters())
             else:
                 self._fg = FlatGradients(self.model.parameters())
             self._flat, self._views = self._fg.flat, self._fg.views

@@ -43,6 +43,11 @@ def _import(handle):
     return int(out.value)
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank cannot allocate, export or map the peer buffers (the decision is agreed through
+    the process group, so callers can fall back to NCCL consistently)."""
+
+
 class PeerAllReduce:
     """`flat` (float32 [numel], numel % 4 == 0) lives in peer-mapped memory; all_reduce_(scale) makes it
     scale * (sum over ranks) on every rank, bit-identically, with one kernel on the current stream.  Every rank must
@@ -59,23 +64,39 @@ class PeerAllReduce:
         self.ctas = int(ctas if ctas is not None else os.environ.get('MGNNS_P2P_CTAS', '96'))
         self.device = torch.device(device)
         with torch.cuda.device(self.device):
-            self._buf = _alloc(4 * max(self.numel, 4))
-            self._flags = _alloc(_lib.mgnns_p2p_flag_bytes())
-            mine = (_export(self._buf), _export(self._flags))
+            ok, err, mine = True, None, None
+            try:
+                self._buf = _alloc(4 * max(self.numel, 4))
+                self._flags = _alloc(_lib.mgnns_p2p_flag_bytes())
+                mine = (_export(self._buf), _export(self._flags))
+            except Exception as exc:                                   # agreed on below: nobody is left in a collective
+                ok, err = False, str(exc)
+            if os.environ.get('MGNNS_P2P_FAIL_RANK') == str(self.rank):  # test hook for the fallback path
+                ok, err, mine = False, 'forced failure (MGNNS_P2P_FAIL_RANK)', None
             handles = [None] * self.world
-            dist.all_gather_object(handles, mine, group=group)     # also a barrier: every allocation is zeroed by now
+            dist.all_gather_object(handles, (ok, err, mine), group=group)   # also a barrier: every allocation is zeroed by now
+            bad = [(q, h[1]) for q, h in enumerate(handles) if not h[0]]
+            if bad:
+                raise PeerMemoryUnavailable("rank %d could not set up its peer-mapped buffers: %s" % bad[0])
             bufs, flags = [], []
             self._imported = []
-            for q, (hb, hf) in enumerate(handles):
-                if q == self.rank:
-                    bufs.append(self._buf)
-                    flags.append(self._flags)
-                else:
-                    pb, pf = _import(hb), _import(hf)
-                    self._imported += [pb, pf]
-                    bufs.append(pb)
-                    flags.append(pf)
-            dist.barrier(group=group)                               # nobody launches before everybody has mapped
+            try:
+                for q, (_, _, (hb, hf)) in enumerate(handles):
+                    if q == self.rank:
+                        bufs.append(self._buf)
+                        flags.append(self._flags)
+                    else:
+                        pb, pf = _import(hb), _import(hf)
+                        self._imported += [pb, pf]
+                        bufs.append(pb)
+                        flags.append(pf)
+            except Exception as exc:
+                ok, err = False, str(exc)
+            agreed = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)     # nobody launches before everybody has mapped
+            if int(agreed.item()) == 0:
+                raise PeerMemoryUnavailable("a rank could not map its peers' buffers through CUDA IPC%s"
+                                            % (": " + err if err else ""))
         self._bufs = (ctypes.c_uint64 * self.world)(*bufs)
         self._flagv = (ctypes.c_uint64 * self.world)(*flags)
         self._holder = _RawCuda(self._buf, self.numel, "<f4")
