@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_ffma.cu", "spmm.cu", "text_gcn.cu", "attention.cu", "small_ops.cu", "tc_gemm.cu", "tc_linear.cu", "lstm.cu", "gcn_fused.cu", "pmi_sparse.cu", "count_ops.cu", "attention_tc.cu", "spmm_hub.cu", "optim.cu"]
+SOURCES = ["gemm_ffma.cu", "spmm.cu", "text_gcn.cu", "attention.cu", "small_ops.cu", "tc_gemm.cu", "tc_linear.cu", "lstm.cu", "gcn_fused.cu", "pmi_sparse.cu", "count_ops.cu", "attention_tc.cu", "spmm_hub.cu", "optim.cu", "p2p_allreduce.cu", "text_bank_ops.cu"]
 HEADERS = ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "mgnns_b200.h")]
 LIB = os.path.join(HERE, "libmgnns_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
